@@ -1,0 +1,188 @@
+/*
+ * p3d_b200.h — C ABI of libp3d_b200.so: the B200 (sm_100a) implementation of Paddle3D's
+ * point-cloud-to-BEV hot path.  This is the drop-in boundary: every entry point below is what a
+ * Paddle custom-op kernel function (PD_BUILD_OP ... SetKernelFn) for this path binds to; the
+ * reference interface each one replaces is cited as file:line under PaddlePaddle/Paddle3D @ 3259dabe.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no C++/torch/paddle types.
+ *   - unless a name ends in `_host`, every data pointer is a DEVICE pointer; attribute arrays
+ *     (voxel_size, point_cloud_range, ...) are HOST pointers read before the launch.
+ *   - `stream` is a cudaStream_t passed as void*.  Calls only enqueue work: they never allocate,
+ *     never synchronise and never touch the default stream.  Data-dependent counts are written to
+ *     device scalars; the caller reads them back when (and if) it needs them.
+ *   - scratch memory is caller-provided: `p3d_<op>_workspace_bytes(...)` gives the size, any
+ *     256-byte aligned device buffer of at least that size works, contents need not be preserved.
+ *   - return value: 0 on success, negative p3d_status on failure (never throws).
+ *     p3d_status_string() gives the message a PD_THROW would carry.
+ */
+#ifndef P3D_B200_H_
+#define P3D_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void *p3d_stream_t; /* cudaStream_t */
+
+enum p3d_status {
+  P3D_OK = 0,
+  P3D_ERR_INVALID_ARG = -1,   /* bad shape / null pointer / unsupported attribute */
+  P3D_ERR_WORKSPACE = -2,     /* workspace_bytes smaller than p3d_*_workspace_bytes() */
+  P3D_ERR_CUDA = -3,          /* a CUDA runtime call or launch failed (see p3d_last_cuda_error) */
+  P3D_ERR_UNSUPPORTED = -4    /* valid in the reference but outside this build's limits */
+};
+
+const char *p3d_status_string(int status);
+int p3d_last_cuda_error(void); /* cudaError_t of the last P3D_ERR_CUDA on this thread */
+int p3d_abi_version(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * hard_voxelize      replaces paddle3d/ops/voxel/voxelize_op.cc:149-166 (op `hard_voxelize`,
+ *                    registration :183-191; CUDA path voxelize_op.cu:208-346).
+ * Semantics are those of the reference CPU kernel (voxelize_op.cc:19-82), deterministically:
+ * voxels numbered in first-appearance order of their first point, capped at max_voxels; each voxel
+ * keeps its first max_points points in input order.
+ *   points               [num_points, num_point_dim] fp32 (num_point_dim >= 3)
+ *   voxel_size_host[3], point_cloud_range_host[6]     attrs
+ *   voxels               [max_voxels, max_points, num_point_dim] fp32, fully written (zero padded)
+ *   coords               [max_voxels, 3] int32 (z, y, x), zero beyond num_voxels
+ *   num_points_per_voxel [max_voxels] int32, zero beyond num_voxels
+ *   num_voxels           [1] int32
+ * ------------------------------------------------------------------------------------------- */
+size_t p3d_hard_voxelize_workspace_bytes(int64_t num_points, int max_points, int max_voxels);
+int p3d_hard_voxelize(const float *points, int64_t num_points, int num_point_dim, const float *voxel_size_host,
+                      const float *point_cloud_range_host, int max_points, int max_voxels, float *voxels,
+                      int32_t *coords, int32_t *num_points_per_voxel, int32_t *num_voxels, void *workspace,
+                      size_t workspace_bytes, p3d_stream_t stream);
+
+/* Fused front end used by the CenterPoint pipeline: hard_voxelize + VoxelMean
+ * (paddle3d/models/voxel_encoders/voxel_encoder.py:49-57) + HardVoxelizer's batch-id pad
+ * (paddle3d/models/voxelizers/voxelize.py:39-58) without materialising the padded voxels tensor.
+ *   mean   [max_voxels, num_point_dim] fp32 (rows >= num_voxels zero)
+ *   coors4 [max_voxels, 4] int32 (batch_id, z, y, x)  */
+int p3d_voxelize_mean(const float *points, int64_t num_points, int num_point_dim, const float *voxel_size_host,
+                      const float *point_cloud_range_host, int max_points, int max_voxels, int batch_id,
+                      float *mean, int32_t *coors4, int32_t *num_points_per_voxel, int32_t *num_voxels,
+                      void *workspace, size_t workspace_bytes, p3d_stream_t stream);
+
+/* VoxelMean alone: voxels [num_voxels_cap, max_points, F] -> mean [num_voxels_cap, F]; rows whose
+ * index >= *num_voxels_dev (device scalar, may be NULL = all rows) are written as zero. */
+int p3d_voxel_mean(const float *voxels, const int32_t *num_points_per_voxel, const int32_t *num_voxels_dev,
+                   int num_voxels_cap, int max_points, int num_point_dim, float *mean, p3d_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * pillar_scatter / sparse to_dense     replaces PointPillarsScatter.forward_batch
+ *   (paddle3d/models/middle_encoders/pillar_scatter.py:57-105: zeros + paddle.scatter + transpose)
+ *   and SparseResNet3D's to_dense + transpose + reshape (sparse_resnet.py:202-206).
+ *   feats  [n, C] fp32;  coords [n, 4] int32 (batch, z, y, x);  n_dev: device count (NULL = n_cap)
+ *   out    [batch, C, D, ny, nx] fp32 fully written; a pillar canvas is the D == 1 case and uses
+ *          index y*nx + x (z ignored), later rows win on duplicate cells.
+ * ------------------------------------------------------------------------------------------- */
+size_t p3d_scatter_dense_workspace_bytes(int batch, int D, int ny, int nx);
+int p3d_scatter_dense(const float *feats, const int32_t *coords, const int32_t *n_dev, int n_cap, int C,
+                      int batch, int D, int ny, int nx, int use_z, float *out, void *workspace,
+                      size_t workspace_bytes, p3d_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * bev_pool_v2 / bev_pool_v2_bkwd      replace paddle3d/ops/bev_pool_v2/bev_pool.cc:30-54, :56-96
+ *   (registrations :111-118 and ops/bev_pool_v2_backward/bev_pool_bkwd.cc:75-80; kernels
+ *   bev_pool_cuda.cu:18-96).  NOTE the reference argument order: lengths before starts.
+ *   depth [B*N, D, H, W] fp32 (flat-indexed by ranks_depth); feat [B*N, H, W, C] fp32;
+ *   ranks_* [n_points] int32; interval_* [n_intervals] int32; out [out_numel] fp32 zero-filled here.
+ * ------------------------------------------------------------------------------------------- */
+int p3d_bev_pool_v2(const float *depth, const float *feat, const int32_t *ranks_depth, const int32_t *ranks_feat,
+                    const int32_t *ranks_bev, const int32_t *interval_lengths, const int32_t *interval_starts,
+                    int n_intervals, int c, float *out, int64_t out_numel, p3d_stream_t stream);
+int p3d_bev_pool_v2_bkwd(const float *out_grad, const float *depth, const float *feat, const int32_t *ranks_depth,
+                         const int32_t *ranks_feat, const int32_t *ranks_bev, const int32_t *interval_lengths,
+                         const int32_t *interval_starts, int n_intervals, int c, float *depth_grad,
+                         int64_t depth_numel, float *feat_grad, int64_t feat_numel, p3d_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * iou3d_nms      replaces paddle3d/ops/iou3d_nms/iou3d_nms.cpp:44-204 (registrations
+ *                iou3d_nms_api.cpp:73-108).  boxes are [n, 7] = x, y, z, dx, dy, dz, heading.
+ * ------------------------------------------------------------------------------------------- */
+int p3d_boxes_overlap_bev(const float *boxes_a, int num_a, const float *boxes_b, int num_b, float *overlap,
+                          p3d_stream_t stream);
+int p3d_boxes_iou_bev(const float *boxes_a, int num_a, const float *boxes_b, int num_b, float *iou,
+                      p3d_stream_t stream);
+/* nms_gpu / nms_normal_gpu: boxes already sorted by score.  keep [n] int32 (first *num_keep valid),
+ * num_keep [1] int32 — both on the DEVICE (the reference finishes on the host; here the greedy
+ * reduction runs on the GPU with no sync).  normal != 0 selects the axis-aligned IoU. */
+size_t p3d_nms_workspace_bytes(int n);
+int p3d_nms(const float *boxes, int n, float nms_overlap_thresh, int normal, int32_t *keep, int32_t *num_keep,
+            void *workspace, size_t workspace_bytes, p3d_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * centerpoint_postprocess      replaces paddle3d/ops/centerpoint_postprocess/postprocess.cc:34-104
+ *                              (postprocess_gpu, postprocess.cu:104-280), batch size 1.
+ *   hm/reg/height/dim/vel/rot: HOST arrays of T device pointers to the per-task NCHW tensors
+ *   hm_channels_host[T]; attrs as in the op.  num_classes_host[T] are the label offsets.
+ *   Outputs (device), sized for the worst case rows_cap = T * max(nms_post_max_size, 1):
+ *     bboxes [rows_cap, 9 or 7], scores [rows_cap], labels [rows_cap] int64,
+ *     counts [T + 1] int32: rows per task, then the total number of valid rows.
+ *   Score-sort tie order is defined as ascending cell index.
+ * ------------------------------------------------------------------------------------------- */
+size_t p3d_centerpoint_postprocess_workspace_bytes(int num_tasks, int feat_h, int feat_w, int nms_pre_max_size,
+                                                    int nms_post_max_size);
+int p3d_centerpoint_postprocess(int num_tasks, const float *const *hm, const int32_t *hm_channels_host,
+                                const float *const *reg, const float *const *height, const float *const *dim,
+                                const float *const *vel, const float *const *rot, int feat_h, int feat_w,
+                                const float *voxel_size_host, const float *point_cloud_range_host,
+                                const float *post_center_range_host, const int32_t *num_classes_host,
+                                int down_ratio, float score_threshold, float nms_iou_threshold,
+                                int nms_pre_max_size, int nms_post_max_size, int with_velocity, float *bboxes,
+                                float *scores, int64_t *labels, int32_t *counts, void *workspace,
+                                size_t workspace_bytes, p3d_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Sparse 3-D convolution      replaces the paddle.sparse.nn layer calls made by SparseResNet3D /
+ *   SparseNet3D (paddle3d/models/middle_encoders/sparse_resnet.py:31-60,84-111,125-206;
+ *   sparsenet.py:38-52,75-155): SubmConv3D / Conv3D (+ BatchNorm(eval) + residual add + ReLU fused).
+ *
+ * Rulebook ("neighbour map") build.  coords are [n, 4] int32 (batch, z, y, x); spatial = (D, H, W).
+ *   p3d_sparse_rulebook_subm : nbr [n_cap, K] int32, nbr[i][k] = input row at coord(i) - pad + k or -1
+ *                              (K = kD*kH*kW, pad = k/2; shared by every SubM layer of a stage).
+ *   p3d_sparse_rulebook_conv : strided Conv3D: writes the output coordinate list out_coords
+ *                              [out_cap, 4] (site order is unspecified), the device counters
+ *                              n_out_dev (int32[4]) and nbr [out_cap, K] with
+ *                              nbr[o][k] = input row at o*stride - pad + k or -1.
+ *   n_in_dev / n_out_dev are device scalars so the whole backbone runs without a host sync.
+ *   n_out_dev[0] = number of output sites (clamped to out_cap), n_out_dev[1] = 1 if sites were
+ *   dropped because out_cap was too small, n_out_dev[2] = unclamped count, n_out_dev[3] reserved.
+ * ------------------------------------------------------------------------------------------- */
+size_t p3d_sparse_rulebook_workspace_bytes(int64_t n_in_cap, int64_t n_out_cap);
+int p3d_sparse_rulebook_subm(const int32_t *coords, const int32_t *n_in_dev, int64_t n_in_cap, int batch,
+                             const int *spatial_host, const int *ksize_host, int32_t *nbr, void *workspace,
+                             size_t workspace_bytes, p3d_stream_t stream);
+int p3d_sparse_rulebook_conv(const int32_t *coords, const int32_t *n_in_dev, int64_t n_in_cap, int batch,
+                             const int *spatial_host, const int *ksize_host, const int *stride_host,
+                             const int *pad_host, int32_t *out_coords, int32_t *n_out_dev, int64_t out_cap,
+                             int32_t *nbr, void *workspace, size_t workspace_bytes, p3d_stream_t stream);
+
+/* Unfused elementwise epilogue (BatchNorm(eval) / sparse.add / ReLU on a materialised tensor):
+ *   out[r, c] = act(x[r, c] * scale[c] + shift[c] (+ residual[r, c])); out may alias x. */
+int p3d_sparse_affine_act(const float *x, const int32_t *n_dev, int64_t n_cap, int C, const float *scale,
+                          const float *shift, const float *residual, int relu, float *out, p3d_stream_t stream);
+
+/* Gather-GEMM-scatter in output-stationary form:
+ *   out[o, :] = act( (sum_k in[nbr[o][k], :] @ W[k]) * scale + shift (+ residual[o, :]) )
+ *   in [n_in, Cin] fp32; W [K, Cin, Cout] fp32 (Paddle's [kD,kH,kW,Cin,Cout]); scale/shift [Cout]
+ *   (BatchNorm(eval) and conv bias folded by the caller; NULL = identity); residual [n_out, Cout] or
+ *   NULL; relu != 0 applies max(.,0).  n_out_dev: device row count (NULL = n_out_cap rows).
+ *   precision: P3D_CONV_FP32 = fp32 FMA on CUDA cores; P3D_CONV_TF32X3 = tcgen05 tensor cores with
+ *   3xTF32 split accumulation in TMEM (fp32-level accuracy). */
+enum p3d_conv_precision { P3D_CONV_FP32 = 0, P3D_CONV_TF32X3 = 1 };
+int p3d_sparse_conv_gather_gemm(const float *in, const int32_t *nbr, const int32_t *n_out_dev, int64_t n_out_cap,
+                                int K, int Cin, int Cout, const float *weight, const float *scale,
+                                const float *shift, const float *residual, int relu, int precision, float *out,
+                                p3d_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* P3D_B200_H_ */

@@ -1,0 +1,54 @@
+// Shared helpers for libp3d_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "p3d_b200.h"
+
+namespace p3d {
+
+extern thread_local int g_last_cuda_error;
+
+inline int cuda_fail(cudaError_t e) {
+  g_last_cuda_error = static_cast<int>(e);
+  return P3D_ERR_CUDA;
+}
+
+#define P3D_CUDA_CHECK(expr)                                \
+  do {                                                      \
+    cudaError_t _e = (expr);                                \
+    if (_e != cudaSuccess) return ::p3d::cuda_fail(_e);     \
+  } while (0)
+#define P3D_LAUNCH_CHECK() P3D_CUDA_CHECK(cudaGetLastError())
+
+constexpr size_t kAlign = 256;
+inline size_t align_up(size_t x, size_t a = kAlign) { return (x + a - 1) / a * a; }
+
+// Sequential carve-out of a caller-provided workspace (also used to size it).
+struct Carver {
+  char *base;
+  size_t off = 0;
+  explicit Carver(void *p) : base(static_cast<char *>(p)) {}
+  template <typename T>
+  T *take(size_t count) {
+    T *r = reinterpret_cast<T *>(base + off);
+    off += align_up(count * sizeof(T));
+    return r;
+  }
+};
+
+inline unsigned int div_up(long long a, long long b) { return static_cast<unsigned int>((a + b - 1) / b); }
+inline uint32_t next_pow2(uint64_t x) {
+  uint32_t p = 1;
+  while (p < x) p <<= 1;
+  return p;
+}
+
+constexpr int kNumSMs = 148;  // B200
+
+__device__ __forceinline__ uint32_t hash32(uint32_t k) {
+  k *= 0x9E3779B1u;  // Fibonacci hashing; callers take the top bits
+  return k;
+}
+
+}  // namespace p3d

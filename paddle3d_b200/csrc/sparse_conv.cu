@@ -1,0 +1,414 @@
+// Sparse 3-D convolution for sm_100a: rulebook build + output-stationary gather-GEMM.
+//
+// Replaces what SparseResNet3D asks of paddle.sparse.nn (sparse_resnet.py:31-60,84-111,125-206):
+// Paddle's phi kernels build a pair list per kernel offset and run K rounds of
+// gather -> cuBLAS GEMM -> scatter-add through HBM.  Here a conv is ONE kernel over an
+// output-stationary neighbour map nbr[n_out, K] (row of the input feeding tap k of output o, or -1):
+//
+//     out[o, :] = act( (sum_k in[nbr[o][k], :] @ W[k]) * scale + shift (+ residual[o, :]) )
+//
+// so every output row is written once, the sum over taps runs in a fixed order (bit-reproducible
+// regardless of row numbering), BatchNorm(eval)/bias/residual/ReLU are fused in the epilogue, and
+// the map is built once per stage and shared by all SubM layers of the stage (the reference's
+// `key='resN'`, sparse_resnet.py:44,130-158).
+//
+// Rulebook build = open-addressing hash of the active coordinates (64-bit entries
+// (linear cell << 32 | row)), all counts kept on the device.
+//
+// This file holds the fp32 CUDA-core GEMM path (exact fp32 FMA accumulation, used for parity and
+// for the 5-channel input layer); the tcgen05 3xTF32 path lives in sparse_conv_tc.cu.
+#include "common.cuh"
+
+namespace p3d {
+namespace {
+
+constexpr unsigned long long kEmpty = ~0ull;
+
+struct Dims {
+  int B, D, H, W;          // input spatial
+  int kd, kh, kw;          // kernel
+  int sd, sh, sw;          // stride
+  int pd, ph, pw;          // padding
+  int oD, oH, oW;          // output spatial
+};
+
+struct RbWs {
+  unsigned long long *tab_in;   // [cap_in]
+  unsigned long long *tab_out;  // [cap_out]
+  uint32_t cap_in, shift_in, cap_out, shift_out;
+  size_t bytes;
+};
+
+RbWs carve_rb(void *p, int64_t n_in_cap, int64_t n_out_cap) {
+  RbWs w;
+  Carver c(p);
+  w.cap_in = next_pow2(static_cast<uint64_t>(n_in_cap > 512 ? n_in_cap : 512) * 2);
+  w.cap_out = next_pow2(static_cast<uint64_t>(n_out_cap > 512 ? n_out_cap : 512) * 2);
+  w.shift_in = 32;
+  for (uint32_t x = w.cap_in; x > 1; x >>= 1) --w.shift_in;
+  w.shift_out = 32;
+  for (uint32_t x = w.cap_out; x > 1; x >>= 1) --w.shift_out;
+  w.tab_in = c.take<unsigned long long>(w.cap_in);
+  w.tab_out = c.take<unsigned long long>(w.cap_out);
+  w.bytes = c.off;
+  return w;
+}
+
+__device__ __forceinline__ uint32_t lin(int b, int z, int y, int x, int D, int H, int W) {
+  return ((static_cast<uint32_t>(b) * D + z) * H + y) * W + x;
+}
+
+__device__ __forceinline__ int lookup(const unsigned long long *__restrict__ tab, uint32_t mask, uint32_t shift,
+                                      uint32_t key) {
+  uint32_t h = hash32(key) >> shift;
+  while (true) {
+    const unsigned long long e = tab[h];
+    if (e == kEmpty) return -1;
+    if (static_cast<uint32_t>(e >> 32) == key) return static_cast<int>(static_cast<uint32_t>(e));
+    h = (h + 1) & mask;
+  }
+}
+
+__global__ void __launch_bounds__(256) rb_insert_kernel(const int32_t *__restrict__ coords,
+                                                        const int32_t *__restrict__ n_dev, int n_cap, Dims d,
+                                                        unsigned long long *__restrict__ tab, uint32_t mask,
+                                                        uint32_t shift) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int n = n_dev ? min(n_dev[0], n_cap) : n_cap;
+  if (i >= n) return;
+  const int4 c = *reinterpret_cast<const int4 *>(coords + static_cast<size_t>(i) * 4);
+  if (c.x < 0 || c.x >= d.B || c.y < 0 || c.y >= d.D || c.z < 0 || c.z >= d.H || c.w < 0 || c.w >= d.W) return;
+  const uint32_t key = lin(c.x, c.y, c.z, c.w, d.D, d.H, d.W);
+  const unsigned long long want = (static_cast<unsigned long long>(key) << 32) | static_cast<uint32_t>(i);
+  uint32_t h = hash32(key) >> shift;
+  while (true) {
+    unsigned long long cur = tab[h];
+    if (cur == kEmpty) {
+      cur = atomicCAS(&tab[h], kEmpty, want);
+      if (cur == kEmpty) return;
+    }
+    if (static_cast<uint32_t>(cur >> 32) == key) {
+      atomicMax(&tab[h], want);  // duplicate coordinate: the later row wins
+      return;
+    }
+    h = (h + 1) & mask;
+  }
+}
+
+// nbr[o][k] = row of the input at  o*stride - pad + k   (SubM: stride 1, pad k/2, o == i)
+__global__ void __launch_bounds__(256) rb_neighbors_kernel(const int32_t *__restrict__ out_coords,
+                                                           const int32_t *__restrict__ n_dev, long long n_cap, Dims d,
+                                                           const unsigned long long *__restrict__ tab, uint32_t mask,
+                                                           uint32_t shift, int subm, int32_t *__restrict__ nbr) {
+  const int K = d.kd * d.kh * d.kw;
+  const long long q = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long n = n_dev ? min(static_cast<long long>(n_dev[0]), n_cap) : n_cap;
+  if (q >= n * K) return;
+  const int o = static_cast<int>(q / K), k = static_cast<int>(q - static_cast<long long>(o) * K);
+  const int4 c = *reinterpret_cast<const int4 *>(out_coords + static_cast<size_t>(o) * 4);
+  const int kz = k / (d.kh * d.kw), ky = (k / d.kw) % d.kh, kx = k % d.kw;
+  const int iz = c.y * d.sd - d.pd + kz, iy = c.z * d.sh - d.ph + ky, ix = c.w * d.sw - d.pw + kx;
+  int r = -1;
+  if (subm && kz == d.kd / 2 && ky == d.kh / 2 && kx == d.kw / 2) {
+    r = o;
+  } else if (iz >= 0 && iz < d.D && iy >= 0 && iy < d.H && ix >= 0 && ix < d.W) {
+    r = lookup(tab, mask, shift, lin(c.x, iz, iy, ix, d.D, d.H, d.W));
+  }
+  nbr[q] = r;
+}
+
+// Strided conv: enumerate output sites.  Thread (i, k): candidate o = (in + pad - k) / stride.
+__global__ void __launch_bounds__(256) rb_outputs_kernel(const int32_t *__restrict__ coords,
+                                                         const int32_t *__restrict__ n_dev, long long n_cap, Dims d,
+                                                         unsigned long long *__restrict__ tab_out, uint32_t mask,
+                                                         uint32_t shift, int32_t *__restrict__ out_coords,
+                                                         int32_t *__restrict__ n_out_dev, int out_cap) {
+  const int K = d.kd * d.kh * d.kw;
+  const long long q = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long n = n_dev ? min(static_cast<long long>(n_dev[0]), n_cap) : n_cap;
+  if (q >= n * K) return;
+  const int i = static_cast<int>(q / K), k = static_cast<int>(q - static_cast<long long>(i) * K);
+  const int4 c = *reinterpret_cast<const int4 *>(coords + static_cast<size_t>(i) * 4);
+  const int kz = k / (d.kh * d.kw), ky = (k / d.kw) % d.kh, kx = k % d.kw;
+  int oz = c.y + d.pd - kz, oy = c.z + d.ph - ky, ox = c.w + d.pw - kx;
+  if (oz < 0 || oy < 0 || ox < 0 || oz % d.sd || oy % d.sh || ox % d.sw) return;
+  oz /= d.sd;
+  oy /= d.sh;
+  ox /= d.sw;
+  if (oz >= d.oD || oy >= d.oH || ox >= d.oW) return;
+  const uint32_t key = lin(c.x, oz, oy, ox, d.oD, d.oH, d.oW);
+  uint32_t h = hash32(key) >> shift;
+  while (true) {
+    unsigned long long cur = tab_out[h];
+    if (cur == kEmpty) {
+      // claim the slot with a provisional row id; the winner numbers the site
+      const unsigned long long want = (static_cast<unsigned long long>(key) << 32) | 0xfffffffeu;
+      cur = atomicCAS(&tab_out[h], kEmpty, want);
+      if (cur == kEmpty) {
+        const int id = atomicAdd(&n_out_dev[2], 1);  // raw counter; clamped copy is published by rb_finish
+        if (id < out_cap) {
+          int4 oc = make_int4(c.x, oz, oy, ox);
+          *reinterpret_cast<int4 *>(out_coords + static_cast<size_t>(id) * 4) = oc;
+        }
+        return;
+      }
+    }
+    if (static_cast<uint32_t>(cur >> 32) == key) return;
+    h = (h + 1) & mask;
+  }
+}
+
+__global__ void rb_finish_kernel(int32_t *n_out_dev, int out_cap) {
+  const int raw = n_out_dev[2];
+  n_out_dev[0] = raw < out_cap ? raw : out_cap;
+  n_out_dev[1] = raw > out_cap ? 1 : 0;
+}
+
+// ------------------------------------------------------------------ fp32 gather-GEMM
+constexpr int TM = 64, TN = 64, KC = 16, LDA = TM + 4;
+
+__global__ void __launch_bounds__(256) gather_gemm_fp32_kernel(const float *__restrict__ in,
+                                                               const int32_t *__restrict__ nbr,
+                                                               const int32_t *__restrict__ n_out_dev, long long n_cap,
+                                                               int K, int Cin, int Cout,
+                                                               const float *__restrict__ weight,
+                                                               const float *__restrict__ scale,
+                                                               const float *__restrict__ shift,
+                                                               const float *__restrict__ residual, int relu,
+                                                               float *__restrict__ out) {
+  extern __shared__ int s_nbr[];                  // [TM][K]
+  __shared__ __align__(16) float As[KC * LDA];   // [kc][row]
+  __shared__ __align__(16) float Bs[KC * TN];    // [kc][col]
+  const long long n = n_out_dev ? min(static_cast<long long>(n_out_dev[0]), n_cap) : n_cap;
+  const long long row0 = static_cast<long long>(blockIdx.x) * TM;
+  if (row0 >= n) return;
+  const int col0 = blockIdx.y * TN;
+  const int rows = static_cast<int>(min(static_cast<long long>(TM), n - row0));
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  for (int q = tid; q < TM * K; q += 256) s_nbr[q] = (q < rows * K) ? nbr[row0 * K + q] : -1;
+  __syncthreads();
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  const bool vecA = (Cin % 4 == 0);
+  const int a_row = tid >> 2, a_seg = tid & 3;  // 64 rows x 4 segments of 4 channels
+  for (int k = 0; k < K; ++k) {
+    const int my = s_nbr[a_row * K + k];
+    if (!__syncthreads_or(my >= 0)) continue;  // no row of this tile has tap k
+    for (int c0 = 0; c0 < Cin; c0 += KC) {
+      // gather A chunk
+      float4 av = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (my >= 0) {
+        const float *src = in + static_cast<size_t>(my) * Cin + c0 + a_seg * 4;
+        if (vecA) {
+          if (c0 + a_seg * 4 < Cin) av = __ldg(reinterpret_cast<const float4 *>(src));
+        } else {
+          const int left = Cin - (c0 + a_seg * 4);
+          if (left > 0) av.x = __ldg(src);
+          if (left > 1) av.y = __ldg(src + 1);
+          if (left > 2) av.z = __ldg(src + 2);
+          if (left > 3) av.w = __ldg(src + 3);
+        }
+      }
+      As[(a_seg * 4 + 0) * LDA + a_row] = av.x;
+      As[(a_seg * 4 + 1) * LDA + a_row] = av.y;
+      As[(a_seg * 4 + 2) * LDA + a_row] = av.z;
+      As[(a_seg * 4 + 3) * LDA + a_row] = av.w;
+      // weight chunk W[k][c0 + r][col0 + c]
+      for (int q = tid; q < KC * TN; q += 256) {
+        const int r = q / TN, c = q - r * TN;
+        float w = 0.f;
+        if (c0 + r < Cin && col0 + c < Cout) w = __ldg(weight + (static_cast<size_t>(k) * Cin + c0 + r) * Cout + col0 + c);
+        Bs[q] = w;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int kk = 0; kk < KC; ++kk) {
+        const float4 a = *reinterpret_cast<const float4 *>(&As[kk * LDA + ty * 4]);
+        const float4 b = *reinterpret_cast<const float4 *>(&Bs[kk * TN + tx * 4]);
+        const float ar[4] = {a.x, a.y, a.z, a.w}, br[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ar[i], br[j], acc[i][j]);
+      }
+      __syncthreads();
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int r = ty * 4 + i;
+    if (r >= rows) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int c = col0 + tx * 4 + j;
+      if (c >= Cout) continue;
+      float v = acc[i][j];
+      if (scale) v = v * scale[c];
+      if (shift) v = v + shift[c];
+      if (residual) v = v + residual[(row0 + r) * Cout + c];
+      if (relu) v = fmaxf(v, 0.f);
+      out[(row0 + r) * Cout + c] = v;
+    }
+  }
+}
+
+// Unfused epilogue for API completeness (paddle.sparse.nn.BatchNorm / ReLU / sparse.add applied to an
+// already materialised tensor): out = act(x * scale + shift (+ residual)).
+__global__ void __launch_bounds__(256) rows_affine_act_kernel(const float *__restrict__ x,
+                                                              const int32_t *__restrict__ n_dev, long long n_cap, int C,
+                                                              const float *__restrict__ scale,
+                                                              const float *__restrict__ shift,
+                                                              const float *__restrict__ residual, int relu,
+                                                              float *__restrict__ out) {
+  const long long n = n_dev ? min(static_cast<long long>(n_dev[0]), n_cap) : n_cap;
+  const long long q = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (q >= n * C) return;
+  const int c = static_cast<int>(q % C);
+  float v = x[q];
+  if (scale) v = v * scale[c];
+  if (shift) v = v + shift[c];
+  if (residual) v = v + residual[q];
+  if (relu) v = fmaxf(v, 0.f);
+  out[q] = v;
+}
+
+int make_dims(int batch, const int *sp, const int *ks, const int *st, const int *pd, int subm, Dims *d) {
+  if (!sp || !ks || batch < 1) return P3D_ERR_INVALID_ARG;
+  d->B = batch;
+  d->D = sp[0];
+  d->H = sp[1];
+  d->W = sp[2];
+  d->kd = ks[0];
+  d->kh = ks[1];
+  d->kw = ks[2];
+  if (d->D < 1 || d->H < 1 || d->W < 1 || d->kd < 1 || d->kh < 1 || d->kw < 1) return P3D_ERR_INVALID_ARG;
+  if (subm) {
+    if (!(d->kd & 1) || !(d->kh & 1) || !(d->kw & 1)) return P3D_ERR_UNSUPPORTED;
+    d->sd = d->sh = d->sw = 1;
+    d->pd = d->kd / 2;
+    d->ph = d->kh / 2;
+    d->pw = d->kw / 2;
+    d->oD = d->D;
+    d->oH = d->H;
+    d->oW = d->W;
+  } else {
+    if (!st || !pd) return P3D_ERR_INVALID_ARG;
+    d->sd = st[0];
+    d->sh = st[1];
+    d->sw = st[2];
+    d->pd = pd[0];
+    d->ph = pd[1];
+    d->pw = pd[2];
+    if (d->sd < 1 || d->sh < 1 || d->sw < 1 || d->pd < 0 || d->ph < 0 || d->pw < 0) return P3D_ERR_INVALID_ARG;
+    d->oD = (d->D + 2 * d->pd - d->kd) / d->sd + 1;
+    d->oH = (d->H + 2 * d->ph - d->kh) / d->sh + 1;
+    d->oW = (d->W + 2 * d->pw - d->kw) / d->sw + 1;
+    if (d->oD < 1 || d->oH < 1 || d->oW < 1) return P3D_ERR_INVALID_ARG;
+  }
+  if (static_cast<long long>(batch) * d->D * d->H * d->W >= 0xffffffffll) return P3D_ERR_UNSUPPORTED;
+  if (d->kd * d->kh * d->kw > 125) return P3D_ERR_UNSUPPORTED;
+  return P3D_OK;
+}
+
+}  // namespace
+}  // namespace p3d
+
+using namespace p3d;
+
+extern "C" size_t p3d_sparse_rulebook_workspace_bytes(int64_t n_in_cap, int64_t n_out_cap) {
+  if (n_in_cap < 0 || n_out_cap < 0) return 0;
+  return carve_rb(nullptr, n_in_cap, n_out_cap).bytes;
+}
+
+extern "C" int p3d_sparse_rulebook_subm(const int32_t *coords, const int32_t *n_in_dev, int64_t n_in_cap, int batch,
+                                        const int *spatial_host, const int *ksize_host, int32_t *nbr,
+                                        void *workspace, size_t workspace_bytes, p3d_stream_t stream) {
+  Dims d;
+  int rc = make_dims(batch, spatial_host, ksize_host, nullptr, nullptr, 1, &d);
+  if (rc) return rc;
+  if (n_in_cap < 0 || n_in_cap > 0x7fffffff / 128 || !workspace || (n_in_cap && (!coords || !nbr)))
+    return P3D_ERR_INVALID_ARG;
+  if (reinterpret_cast<uintptr_t>(coords) & 15) return P3D_ERR_INVALID_ARG;
+  if (n_in_cap == 0) return P3D_OK;
+  RbWs w = carve_rb(workspace, n_in_cap, 0);
+  if (workspace_bytes < w.bytes) return P3D_ERR_WORKSPACE;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int K = d.kd * d.kh * d.kw;
+  P3D_CUDA_CHECK(cudaMemsetAsync(w.tab_in, 0xff, sizeof(unsigned long long) * w.cap_in, st));
+  rb_insert_kernel<<<div_up(n_in_cap, 256), 256, 0, st>>>(coords, n_in_dev, static_cast<int>(n_in_cap), d, w.tab_in,
+                                                         w.cap_in - 1, w.shift_in);
+  P3D_LAUNCH_CHECK();
+  rb_neighbors_kernel<<<div_up(n_in_cap * K, 256), 256, 0, st>>>(coords, n_in_dev, n_in_cap, d, w.tab_in,
+                                                                 w.cap_in - 1, w.shift_in, 1, nbr);
+  P3D_LAUNCH_CHECK();
+  return P3D_OK;
+}
+
+extern "C" int p3d_sparse_rulebook_conv(const int32_t *coords, const int32_t *n_in_dev, int64_t n_in_cap, int batch,
+                                        const int *spatial_host, const int *ksize_host, const int *stride_host,
+                                        const int *pad_host, int32_t *out_coords, int32_t *n_out_dev,
+                                        int64_t out_cap, int32_t *nbr, void *workspace, size_t workspace_bytes,
+                                        p3d_stream_t stream) {
+  Dims d;
+  int rc = make_dims(batch, spatial_host, ksize_host, stride_host, pad_host, 0, &d);
+  if (rc) return rc;
+  if (n_in_cap < 0 || out_cap < 1 || n_in_cap > 0x7fffffff / 128 || out_cap > 0x7fffffff / 128 || !workspace ||
+      !n_out_dev || !out_coords || !nbr || (n_in_cap && !coords))
+    return P3D_ERR_INVALID_ARG;
+  if ((reinterpret_cast<uintptr_t>(coords) & 15) || (reinterpret_cast<uintptr_t>(out_coords) & 15))
+    return P3D_ERR_INVALID_ARG;
+  if (static_cast<long long>(batch) * d.oD * d.oH * d.oW >= 0xffffffffll) return P3D_ERR_UNSUPPORTED;
+  RbWs w = carve_rb(workspace, n_in_cap, out_cap);
+  if (workspace_bytes < w.bytes) return P3D_ERR_WORKSPACE;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int K = d.kd * d.kh * d.kw;
+  P3D_CUDA_CHECK(cudaMemsetAsync(w.tab_in, 0xff, sizeof(unsigned long long) * w.cap_in, st));
+  P3D_CUDA_CHECK(cudaMemsetAsync(w.tab_out, 0xff, sizeof(unsigned long long) * w.cap_out, st));
+  P3D_CUDA_CHECK(cudaMemsetAsync(n_out_dev, 0, sizeof(int32_t) * 4, st));
+  if (n_in_cap > 0) {
+    rb_insert_kernel<<<div_up(n_in_cap, 256), 256, 0, st>>>(coords, n_in_dev, static_cast<int>(n_in_cap), d,
+                                                           w.tab_in, w.cap_in - 1, w.shift_in);
+    P3D_LAUNCH_CHECK();
+    rb_outputs_kernel<<<div_up(n_in_cap * K, 256), 256, 0, st>>>(coords, n_in_dev, n_in_cap, d, w.tab_out,
+                                                                 w.cap_out - 1, w.shift_out, out_coords, n_out_dev,
+                                                                 static_cast<int>(out_cap));
+    P3D_LAUNCH_CHECK();
+  }
+  rb_finish_kernel<<<1, 1, 0, st>>>(n_out_dev, static_cast<int>(out_cap));
+  P3D_LAUNCH_CHECK();
+  rb_neighbors_kernel<<<div_up(out_cap * K, 256), 256, 0, st>>>(out_coords, n_out_dev, out_cap, d, w.tab_in,
+                                                               w.cap_in - 1, w.shift_in, 0, nbr);
+  P3D_LAUNCH_CHECK();
+  return P3D_OK;
+}
+
+extern "C" int p3d_sparse_conv_gather_gemm_fp32(const float *in, const int32_t *nbr, const int32_t *n_out_dev,
+                                                int64_t n_out_cap, int K, int Cin, int Cout, const float *weight,
+                                                const float *scale, const float *shift, const float *residual,
+                                                int relu, float *out, p3d_stream_t stream) {
+  if (n_out_cap < 0 || K < 1 || Cin < 1 || Cout < 1 || !weight || (n_out_cap && (!in || !nbr || !out)))
+    return P3D_ERR_INVALID_ARG;
+  if (n_out_cap == 0) return P3D_OK;
+  if ((Cin % 4 == 0) && (reinterpret_cast<uintptr_t>(in) & 15)) return P3D_ERR_INVALID_ARG;
+  const size_t smem = static_cast<size_t>(TM) * K * sizeof(int);
+  if (smem > 40 * 1024) return P3D_ERR_UNSUPPORTED;
+  dim3 grid(div_up(n_out_cap, TM), div_up(Cout, TN));
+  gather_gemm_fp32_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(
+      in, nbr, n_out_dev, n_out_cap, K, Cin, Cout, weight, scale, shift, residual, relu, out);
+  P3D_LAUNCH_CHECK();
+  return P3D_OK;
+}
+
+extern "C" int p3d_sparse_affine_act(const float *x, const int32_t *n_dev, int64_t n_cap, int C, const float *scale,
+                                     const float *shift, const float *residual, int relu, float *out,
+                                     p3d_stream_t stream) {
+  if (n_cap < 0 || C < 1 || (n_cap && (!x || !out))) return P3D_ERR_INVALID_ARG;
+  if (n_cap == 0) return P3D_OK;
+  rows_affine_act_kernel<<<div_up(n_cap * C, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      x, n_dev, n_cap, C, scale, shift, residual, relu, out);
+  P3D_LAUNCH_CHECK();
+  return P3D_OK;
+}

@@ -1,0 +1,444 @@
+// hard_voxelize for sm_100a — deterministic, CPU-semantics exact.
+//
+// Replaces the reference's 7-kernel + cumsum pipeline over three dense 332 MB grids
+// (paddle3d/ops/voxel/voxelize_op.cu:208-346) with a hash of the occupied cells only:
+//
+//   K0 vox_init        table <- EMPTY, scan descriptors <- 0, slot lists <- INF           (one launch)
+//   K1 vox_insert      per point: cell id, open-addressing insert; the 64-bit entry is
+//                      (cell << 32 | point index) and is reduced with one atomicMin, so each
+//                      occupied cell ends up holding its FIRST point — the quantity the CPU
+//                      kernel's first-appearance numbering is built on (voxelize_op.cc:59-69).
+//                      Same-cell lanes of a warp are aggregated with __match_any_sync: only the
+//                      lowest lane (smallest index) touches the table.
+//   K2 vox_rank        single-pass decoupled-look-back scan over "is first point of its cell"
+//                      flags -> voxel id (rank < max_voxels, else dropped: .cc:61-64), coords.
+//   K3 vox_slots       per point: keep the max_points smallest point indices of its voxel, in
+//                      ascending order, with a cascade of atomicMin (deterministic under any
+//                      interleaving: slot s always converges to the (s+1)-th smallest index)
+//                      — the CPU kernel's "first P points in input order" (.cc:71-79).
+//   K4 vox_write       gather-formulated single pass over the outputs: every float4 of
+//                      voxels[max_voxels, P, F] is written exactly once (point value or zero),
+//                      coalesced, plus num_points_per_voxel and the zero tail of coords.
+//                      This is the HBM-roofline kernel: 4NF + 4VPF + 12V + 4V algorithmic bytes.
+//
+// All intermediate state (<= 8*cap + 4*(N + cap + V*P) bytes) is L2-resident on B200.
+#include <limits.h>
+
+#include "common.cuh"
+
+namespace p3d {
+namespace {
+
+constexpr unsigned long long kEmpty = ~0ull;
+constexpr int kInf = 0x7fffffff;
+constexpr int kScanBlock = 1024;
+
+struct VoxGeom {
+  float min_x, min_y, min_z;
+  float vs_x, vs_y, vs_z;
+  int gx, gy, gz;
+};
+
+struct VoxWs {
+  unsigned long long *table;   // [cap] (cell << 32 | first point index)
+  unsigned long long *desc;    // [nblocks + 1]  desc[0] = ticket, desc[1 + b] = (status << 32 | value)
+  int32_t *pt_slot;            // [N] table slot of each point, -1 = outside the grid
+  int32_t *slot_vox;           // [cap] voxel id of an occupied slot (-1 = beyond max_voxels)
+  int32_t *lists;              // [V, P] the P smallest point indices of each voxel, ascending
+  uint32_t cap, shift;
+  unsigned int nblocks;
+  size_t bytes;
+};
+
+VoxWs carve(void *ws, int64_t n, int P, int V) {
+  VoxWs w;
+  Carver c(ws);
+  w.cap = next_pow2(static_cast<uint64_t>(n > 512 ? n : 512) * 2);
+  w.shift = 32;
+  for (uint32_t x = w.cap; x > 1; x >>= 1) --w.shift;
+  w.nblocks = div_up(n > 0 ? n : 1, kScanBlock);
+  w.table = c.take<unsigned long long>(w.cap);
+  w.desc = c.take<unsigned long long>(w.nblocks + 1);
+  w.pt_slot = c.take<int32_t>(n > 0 ? n : 1);
+  w.slot_vox = c.take<int32_t>(w.cap);
+  w.lists = c.take<int32_t>(static_cast<size_t>(V) * P);
+  w.bytes = c.off;
+  return w;
+}
+
+// ---------------------------------------------------------------- K0
+__global__ void vox_init_kernel(uint4 *table16, size_t n_table16, uint4 *desc16, size_t n_desc16, uint4 *lists16,
+                                size_t n_lists16) {
+  const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
+  const size_t tid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const uint4 ones = make_uint4(~0u, ~0u, ~0u, ~0u);
+  const uint4 zero = make_uint4(0, 0, 0, 0);
+  const uint4 inf = make_uint4(kInf, kInf, kInf, kInf);
+  for (size_t i = tid; i < n_table16; i += stride) table16[i] = ones;
+  for (size_t i = tid; i < n_desc16; i += stride) desc16[i] = zero;
+  for (size_t i = tid; i < n_lists16; i += stride) lists16[i] = inf;
+}
+
+// ---------------------------------------------------------------- K1
+__device__ __forceinline__ int cell_of(const float *__restrict__ pt, const VoxGeom &g) {
+  // fp32 subtract, IEEE fp32 divide, floor — exactly voxelize_op.cc:37-45
+  const int cx = static_cast<int>(floorf(__fdiv_rn(__fsub_rn(pt[0], g.min_x), g.vs_x)));
+  const int cy = static_cast<int>(floorf(__fdiv_rn(__fsub_rn(pt[1], g.min_y), g.vs_y)));
+  const int cz = static_cast<int>(floorf(__fdiv_rn(__fsub_rn(pt[2], g.min_z), g.vs_z)));
+  if (cx < 0 || cx >= g.gx || cy < 0 || cy >= g.gy || cz < 0 || cz >= g.gz) return -1;
+  return (cz * g.gy + cy) * g.gx + cx;
+}
+
+__global__ void __launch_bounds__(256) vox_insert_kernel(const float *__restrict__ points, int n, int F, VoxGeom g,
+                                                         unsigned long long *__restrict__ table, uint32_t mask,
+                                                         uint32_t shift, int32_t *__restrict__ pt_slot) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned active = __ballot_sync(0xffffffffu, i < n);
+  if (i >= n) return;
+  const int cell = cell_of(points + static_cast<size_t>(i) * F, g);
+  // warp aggregation: lanes that fall in the same cell elect their lowest lane (= smallest index)
+  const unsigned peers = __match_any_sync(active, cell);
+  const int leader = __ffs(peers) - 1;
+  const int lane = threadIdx.x & 31;
+  int slot = -1;
+  if (cell >= 0 && lane == leader) {
+    const unsigned long long want = (static_cast<unsigned long long>(cell) << 32) | static_cast<uint32_t>(i);
+    uint32_t h = hash32(static_cast<uint32_t>(cell)) >> shift;
+    while (true) {
+      unsigned long long cur = table[h];
+      if (cur == kEmpty) {
+        cur = atomicCAS(&table[h], kEmpty, want);
+        if (cur == kEmpty) break;
+      }
+      if (static_cast<uint32_t>(cur >> 32) == static_cast<uint32_t>(cell)) {
+        if (want < cur) atomicMin(&table[h], want);
+        break;
+      }
+      h = (h + 1) & mask;
+    }
+    slot = static_cast<int>(h);
+  }
+  slot = __shfl_sync(peers, slot, leader);
+  pt_slot[i] = slot;
+}
+
+// ---------------------------------------------------------------- K2
+__global__ void __launch_bounds__(kScanBlock) vox_rank_kernel(const unsigned long long *__restrict__ table,
+                                                              const int32_t *__restrict__ pt_slot, int n,
+                                                              int max_voxels, VoxGeom g,
+                                                              unsigned long long *__restrict__ desc,
+                                                              int32_t *__restrict__ slot_vox,
+                                                              int32_t *__restrict__ coords, int coord_stride,
+                                                              int coord_off, int batch_id,
+                                                              int32_t *__restrict__ num_voxels) {
+  __shared__ unsigned int s_bid;
+  __shared__ int s_warp[kScanBlock / 32];
+  __shared__ int s_prefix;
+  if (threadIdx.x == 0) s_bid = static_cast<unsigned int>(atomicAdd(&desc[0], 1ull));
+  __syncthreads();
+  const unsigned int bid = s_bid;
+  const int i = static_cast<int>(bid) * kScanBlock + threadIdx.x;
+  int slot = -1, flag = 0;
+  unsigned long long entry = 0;
+  if (i < n) {
+    slot = pt_slot[i];
+    if (slot >= 0) {
+      entry = table[slot];
+      flag = (static_cast<uint32_t>(entry) == static_cast<uint32_t>(i));
+    }
+  }
+  // block exclusive scan of flags
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const unsigned bal = __ballot_sync(0xffffffffu, flag);
+  const int in_warp = __popc(bal & ((1u << lane) - 1));
+  if (lane == 0) s_warp[wid] = __popc(bal);
+  __syncthreads();
+  if (wid == 0) {
+    int v = s_warp[lane];
+    int inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      int t = __shfl_up_sync(0xffffffffu, inc, d);
+      if (lane >= d) inc += t;
+    }
+    s_warp[lane] = inc - v;  // exclusive warp offsets
+    const int aggregate = __shfl_sync(0xffffffffu, inc, 31);
+    if (lane == 0) {
+      // decoupled look-back: status 1 = block aggregate, 2 = inclusive prefix
+      int prefix = 0;
+      volatile unsigned long long *vd = desc + 1;
+      if (bid == 0) {
+        vd[0] = (2ull << 32) | static_cast<uint32_t>(aggregate);
+      } else {
+        vd[bid] = (1ull << 32) | static_cast<uint32_t>(aggregate);
+        int j = static_cast<int>(bid) - 1;
+        while (true) {
+          unsigned long long d = vd[j];
+          const uint32_t st = static_cast<uint32_t>(d >> 32);
+          if (st == 0) continue;
+          prefix += static_cast<int>(static_cast<uint32_t>(d));
+          if (st == 2) break;
+          --j;
+        }
+        vd[bid] = (2ull << 32) | static_cast<uint32_t>(prefix + aggregate);
+      }
+      s_prefix = prefix;
+      if (bid == gridDim.x - 1) {
+        const int total = prefix + aggregate;
+        num_voxels[0] = total < max_voxels ? total : max_voxels;  // voxelize_op.cc:61-64 cap
+      }
+    }
+  }
+  __syncthreads();
+  if (flag) {
+    const int rank = s_prefix + s_warp[wid] + in_warp;
+    const int v = rank < max_voxels ? rank : -1;
+    slot_vox[slot] = v;
+    if (v >= 0) {
+      const int cell = static_cast<int>(entry >> 32);
+      const int cx = cell % g.gx;
+      const int r = cell / g.gx;
+      int32_t *c = coords + static_cast<size_t>(v) * coord_stride;
+      if (coord_off) c[0] = batch_id;
+      c[coord_off + 0] = r / g.gy;  // (z, y, x) order, voxelize_op.cc:66-69
+      c[coord_off + 1] = r % g.gy;
+      c[coord_off + 2] = cx;
+    }
+  }
+}
+
+// ---------------------------------------------------------------- K3
+__global__ void __launch_bounds__(256) vox_slots_kernel(const int32_t *__restrict__ pt_slot,
+                                                        const int32_t *__restrict__ slot_vox, int n, int P,
+                                                        int32_t *__restrict__ lists) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const int slot = pt_slot[i];
+  if (slot < 0) return;
+  const int v = slot_vox[slot];
+  if (v < 0) return;
+  int32_t *L = lists + static_cast<size_t>(v) * P;
+  int cur = i;
+  for (int s = 0; s < P; ++s) {
+    if (L[s] < cur) continue;  // resident is already smaller: it can only shrink further (monotone), skip the atomic
+    const int old = atomicMin(&L[s], cur);
+    if (old == kInf) break;     // landed in a free slot
+    if (old > cur) cur = old;   // displaced a larger index: carry it down
+  }
+}
+
+// ---------------------------------------------------------------- K4
+__device__ __forceinline__ void st_stream(float4 *p, float4 v) { __stcs(p, v); }
+
+__global__ void __launch_bounds__(256) vox_write_kernel(const float *__restrict__ points, int F, int P, int V,
+                                                        const int32_t *__restrict__ lists,
+                                                        const int32_t *__restrict__ num_voxels_dev,
+                                                        float *__restrict__ voxels, int32_t *__restrict__ coords,
+                                                        int32_t *__restrict__ npv, long long total4,
+                                                        long long total) {
+  const long long q = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (q < total4) {
+    const long long e0 = q * 4;
+    const int PF = P * F;
+    int v = static_cast<int>(e0 / PF);
+    int r = static_cast<int>(e0 - static_cast<long long>(v) * PF);
+    int s = r / F;
+    int f = r - s * F;
+    int idx = lists[static_cast<size_t>(v) * P + s];
+    float o[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      o[k] = (idx != kInf) ? __ldg(points + static_cast<size_t>(idx) * F + f) : 0.f;
+      if (++f == F) {
+        f = 0;
+        if (++s == P) {
+          s = 0;
+          ++v;
+        }
+        if (k < 3 && v < V) idx = lists[static_cast<size_t>(v) * P + s];
+      }
+    }
+    st_stream(reinterpret_cast<float4 *>(voxels) + q, make_float4(o[0], o[1], o[2], o[3]));
+  } else if (q == total4) {
+    // scalar tail when V*P*F is not a multiple of 4
+    for (long long e = total4 * 4; e < total; ++e) {
+      const int v = static_cast<int>(e / (P * F));
+      const int r = static_cast<int>(e - static_cast<long long>(v) * P * F);
+      const int idx = lists[static_cast<size_t>(v) * P + r / F];
+      voxels[e] = (idx != kInf) ? points[static_cast<size_t>(idx) * F + r % F] : 0.f;
+    }
+  }
+  if (q < V) {
+    const int v = static_cast<int>(q);
+    int cnt = 0;
+    for (int s = 0; s < P; ++s) cnt += (lists[static_cast<size_t>(v) * P + s] != kInf);
+    npv[v] = cnt;
+    if (v >= num_voxels_dev[0]) {
+      coords[v * 3 + 0] = 0;
+      coords[v * 3 + 1] = 0;
+      coords[v * 3 + 2] = 0;
+    }
+  }
+}
+
+// Fused VoxelMean writer (voxel_encoder.py:49-57): mean over the kept points, summed in slot order.
+__global__ void __launch_bounds__(256) vox_mean_kernel(const float *__restrict__ points, int F, int P, int V,
+                                                       const int32_t *__restrict__ lists,
+                                                       const int32_t *__restrict__ num_voxels_dev,
+                                                       float *__restrict__ mean, int32_t *__restrict__ coors4,
+                                                       int32_t *__restrict__ npv) {
+  const long long q = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (q >= static_cast<long long>(V) * F) return;
+  const int v = static_cast<int>(q / F), f = static_cast<int>(q - static_cast<long long>(v) * F);
+  float s = 0.f;
+  int cnt = 0;
+  for (int k = 0; k < P; ++k) {
+    const int idx = lists[static_cast<size_t>(v) * P + k];
+    if (idx == kInf) break;  // lists are ascending with INF padding
+    s += __ldg(points + static_cast<size_t>(idx) * F + f);
+    ++cnt;
+  }
+  const bool live = v < num_voxels_dev[0];
+  mean[q] = live ? __fdiv_rn(s, static_cast<float>(cnt)) : 0.f;
+  if (f == 0) {
+    npv[v] = cnt;
+    if (!live) {
+      int4 z = make_int4(0, 0, 0, 0);
+      *reinterpret_cast<int4 *>(coors4 + static_cast<size_t>(v) * 4) = z;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) voxel_mean_kernel(const float *__restrict__ voxels,
+                                                         const int32_t *__restrict__ npv,
+                                                         const int32_t *__restrict__ nv_dev, int cap, int P, int F,
+                                                         float *__restrict__ mean) {
+  const long long q = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (q >= static_cast<long long>(cap) * F) return;
+  const int v = static_cast<int>(q / F), f = static_cast<int>(q - static_cast<long long>(v) * F);
+  if (nv_dev && v >= nv_dev[0]) {
+    mean[q] = 0.f;
+    return;
+  }
+  float s = 0.f;
+  for (int k = 0; k < P; ++k) s += voxels[(static_cast<size_t>(v) * P + k) * F + f];
+  mean[q] = __fdiv_rn(s, static_cast<float>(npv[v]));
+}
+
+int check_geom(const float *vs, const float *pcr, int64_t n, int F, int P, int V, VoxGeom *g) {
+  if (!vs || !pcr || n < 0 || n > INT_MAX - kScanBlock || F < 3 || P < 1 || V < 1) return P3D_ERR_INVALID_ARG;
+  g->min_x = pcr[0];
+  g->min_y = pcr[1];
+  g->min_z = pcr[2];
+  g->vs_x = vs[0];
+  g->vs_y = vs[1];
+  g->vs_z = vs[2];
+  // grid = round((max - min) / size) in fp32, voxelize_op.cc:97-102
+  g->gx = static_cast<int>(roundf((pcr[3] - pcr[0]) / vs[0]));
+  g->gy = static_cast<int>(roundf((pcr[4] - pcr[1]) / vs[1]));
+  g->gz = static_cast<int>(roundf((pcr[5] - pcr[2]) / vs[2]));
+  if (g->gx < 1 || g->gy < 1 || g->gz < 1) return P3D_ERR_INVALID_ARG;
+  if (static_cast<double>(g->gx) * g->gy * g->gz >= 2147483648.0) return P3D_ERR_UNSUPPORTED;
+  if (static_cast<long long>(V) * P * F >= (1ll << 40)) return P3D_ERR_UNSUPPORTED;
+  return P3D_OK;
+}
+
+int run_front(const float *points, int n, int F, const VoxGeom &g, int P, int V, const VoxWs &w, int32_t *coords,
+              int coord_stride, int coord_off, int batch_id, int32_t *num_voxels, cudaStream_t st) {
+  const size_t n_t16 = static_cast<size_t>(w.cap) / 2;
+  const size_t n_d16 = (static_cast<size_t>(w.nblocks) + 1 + 1) / 2;  // carve() pads to 256 B
+  const size_t n_l16 = (static_cast<size_t>(V) * P + 3) / 4;
+  vox_init_kernel<<<kNumSMs * 4, 256, 0, st>>>(reinterpret_cast<uint4 *>(w.table), n_t16,
+                                               reinterpret_cast<uint4 *>(w.desc), n_d16,
+                                               reinterpret_cast<uint4 *>(w.lists), n_l16);
+  P3D_LAUNCH_CHECK();
+  if (n > 0) {
+    vox_insert_kernel<<<div_up(n, 256), 256, 0, st>>>(points, n, F, g, w.table, w.cap - 1, w.shift, w.pt_slot);
+    P3D_LAUNCH_CHECK();
+    vox_rank_kernel<<<w.nblocks, kScanBlock, 0, st>>>(w.table, w.pt_slot, n, V, g, w.desc, w.slot_vox, coords,
+                                                      coord_stride, coord_off, batch_id, num_voxels);
+    P3D_LAUNCH_CHECK();
+    vox_slots_kernel<<<div_up(n, 256), 256, 0, st>>>(w.pt_slot, w.slot_vox, n, P, w.lists);
+    P3D_LAUNCH_CHECK();
+  } else {
+    P3D_CUDA_CHECK(cudaMemsetAsync(num_voxels, 0, sizeof(int32_t), st));
+  }
+  return P3D_OK;
+}
+
+}  // namespace
+}  // namespace p3d
+
+using namespace p3d;
+
+extern "C" size_t p3d_hard_voxelize_workspace_bytes(int64_t num_points, int max_points, int max_voxels) {
+  if (num_points < 0 || max_points < 1 || max_voxels < 1) return 0;
+  return carve(nullptr, num_points, max_points, max_voxels).bytes;
+}
+
+extern "C" int p3d_hard_voxelize(const float *points, int64_t num_points, int num_point_dim,
+                                 const float *voxel_size_host, const float *point_cloud_range_host, int max_points,
+                                 int max_voxels, float *voxels, int32_t *coords, int32_t *num_points_per_voxel,
+                                 int32_t *num_voxels, void *workspace, size_t workspace_bytes,
+                                 p3d_stream_t stream) {
+  VoxGeom g;
+  int rc = check_geom(voxel_size_host, point_cloud_range_host, num_points, num_point_dim, max_points, max_voxels, &g);
+  if (rc) return rc;
+  if ((!points && num_points) || !voxels || !coords || !num_points_per_voxel || !num_voxels || !workspace)
+    return P3D_ERR_INVALID_ARG;
+  if ((reinterpret_cast<uintptr_t>(voxels) & 15) || (reinterpret_cast<uintptr_t>(workspace) & 255))
+    return P3D_ERR_INVALID_ARG;
+  const VoxWs w = carve(workspace, num_points, max_points, max_voxels);
+  if (workspace_bytes < w.bytes) return P3D_ERR_WORKSPACE;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int n = static_cast<int>(num_points);
+  rc = run_front(points, n, num_point_dim, g, max_points, max_voxels, w, coords, 3, 0, 0, num_voxels, st);
+  if (rc) return rc;
+  const long long total = static_cast<long long>(max_voxels) * max_points * num_point_dim;
+  const long long total4 = total / 4;
+  long long threads = total4 + 1;
+  if (threads < max_voxels) threads = max_voxels;
+  vox_write_kernel<<<div_up(threads, 256), 256, 0, st>>>(points, num_point_dim, max_points, max_voxels, w.lists,
+                                                        num_voxels, voxels, coords, num_points_per_voxel, total4,
+                                                        total);
+  P3D_LAUNCH_CHECK();
+  return P3D_OK;
+}
+
+extern "C" int p3d_voxelize_mean(const float *points, int64_t num_points, int num_point_dim,
+                                 const float *voxel_size_host, const float *point_cloud_range_host, int max_points,
+                                 int max_voxels, int batch_id, float *mean, int32_t *coors4,
+                                 int32_t *num_points_per_voxel, int32_t *num_voxels, void *workspace,
+                                 size_t workspace_bytes, p3d_stream_t stream) {
+  VoxGeom g;
+  int rc = check_geom(voxel_size_host, point_cloud_range_host, num_points, num_point_dim, max_points, max_voxels, &g);
+  if (rc) return rc;
+  if ((!points && num_points) || !mean || !coors4 || !num_points_per_voxel || !num_voxels || !workspace)
+    return P3D_ERR_INVALID_ARG;
+  if ((reinterpret_cast<uintptr_t>(coors4) & 15) || (reinterpret_cast<uintptr_t>(workspace) & 255))
+    return P3D_ERR_INVALID_ARG;
+  const VoxWs w = carve(workspace, num_points, max_points, max_voxels);
+  if (workspace_bytes < w.bytes) return P3D_ERR_WORKSPACE;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  rc = run_front(points, static_cast<int>(num_points), num_point_dim, g, max_points, max_voxels, w, coors4, 4, 1,
+                 batch_id, num_voxels, st);
+  if (rc) return rc;
+  const long long threads = static_cast<long long>(max_voxels) * num_point_dim;
+  vox_mean_kernel<<<div_up(threads, 256), 256, 0, st>>>(points, num_point_dim, max_points, max_voxels, w.lists,
+                                                       num_voxels, mean, coors4, num_points_per_voxel);
+  P3D_LAUNCH_CHECK();
+  return P3D_OK;
+}
+
+extern "C" int p3d_voxel_mean(const float *voxels, const int32_t *num_points_per_voxel,
+                              const int32_t *num_voxels_dev, int num_voxels_cap, int max_points, int num_point_dim,
+                              float *mean, p3d_stream_t stream) {
+  if (!voxels || !num_points_per_voxel || !mean || num_voxels_cap < 0 || max_points < 1 || num_point_dim < 1)
+    return P3D_ERR_INVALID_ARG;
+  if (num_voxels_cap == 0) return P3D_OK;
+  const long long threads = static_cast<long long>(num_voxels_cap) * num_point_dim;
+  voxel_mean_kernel<<<div_up(threads, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      voxels, num_points_per_voxel, num_voxels_dev, num_voxels_cap, max_points, num_point_dim, mean);
+  P3D_LAUNCH_CHECK();
+  return P3D_OK;
+}

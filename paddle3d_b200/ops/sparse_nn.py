@@ -1,0 +1,296 @@
+"""Drop-in mirror of the `paddle.sparse` surface used by SparseResNet3D / SparseNet3D
+(paddle3d/models/middle_encoders/sparse_resnet.py:22-23,31-60,84-111,125-206; sparsenet.py:38-52):
+
+    nn.SubmConv3D(in, out, kernel_size, stride=1, padding=0, bias_attr=None, key=None)
+    nn.Conv3D(in, out, kernel_size, stride=1, padding=0, bias_attr=None)
+    nn.BatchNorm(num_features, momentum=0.9, epsilon=1e-5)     (inference statistics)
+    nn.ReLU()
+    sparse_coo_tensor(indices[4, nnz], values[nnz, C], shape), add(x, y), x.to_dense()
+
+so the model file only changes its import line (`from paddle3d_b200.ops.sparse_nn import nn, ...`).
+
+Execution model (B200-first, not Paddle's): a convolution does not run when it is called.  It returns
+a tensor with a *pending* fused kernel; BatchNorm / add / ReLU applied to that tensor fold into the
+kernel's epilogue, and the single gather-GEMM launch happens when the values are needed (next conv,
+to_dense, .values()).  conv -> bn -> relu, and conv -> bn -> add -> relu, are one launch each.
+Row counts stay on the device (`num`), buffers are sized by capacity, no host sync anywhere.
+"""
+import math
+
+import numpy as np
+import torch
+
+from .._lib import check, host_ints, lib
+from .._mem import ptr, require_cuda, stream, workspace
+from . import pillar_scatter as _ps
+
+FP32, TF32X3 = 0, 1
+_default_precision = [FP32]
+
+
+def set_precision(p):
+    """FP32 = CUDA-core fp32 FMA; TF32X3 = tcgen05 tensor cores with 3xTF32 split accumulation."""
+    _default_precision[0] = int(p)
+
+
+def _triple(v):
+    return [int(v)] * 3 if np.isscalar(v) else [int(x) for x in v]
+
+
+class _IndexSet:
+    """Active sites of one resolution level: coords [cap, 4] (b, z, y, x), device count, rulebooks."""
+
+    def __init__(self, coords, num, cap, batch, spatial):
+        self.coords, self.num, self.cap, self.batch, self.spatial = coords, num, cap, batch, list(spatial)
+        self.subm_rulebooks = {}
+
+    def subm_rulebook(self, ksize, key):
+        k = (key, tuple(ksize)) if key is not None else ("_anon", tuple(ksize))
+        nbr = self.subm_rulebooks.get(k)
+        if nbr is None:
+            K = ksize[0] * ksize[1] * ksize[2]
+            dev = self.coords.device
+            nbr = torch.empty((self.cap, K), dtype=torch.int32, device=dev)
+            L = lib()
+            ws = workspace(L.p3d_sparse_rulebook_workspace_bytes(self.cap, 0), dev, "rulebook")
+            check(L.p3d_sparse_rulebook_subm(ptr(self.coords), ptr(self.num), self.cap, self.batch,
+                                             host_ints(self.spatial), host_ints(ksize), ptr(nbr), ptr(ws), ws.numel(),
+                                             stream(dev)), "sparse_rulebook_subm")
+            self.subm_rulebooks[k] = nbr
+        return nbr
+
+
+class SparseCooTensor:
+    def __init__(self, index, values=None, channels=None, pending=None):
+        self.index = index
+        self._values = values
+        self._pending = pending
+        self.channels = channels if channels is not None else values.shape[1]
+
+    # ---- paddle-like surface
+    @property
+    def shape(self):
+        return [self.index.batch] + self.index.spatial + [self.channels]
+
+    def values(self):
+        if self._pending is not None:
+            self._values = _run(self._pending)
+            self._pending = None
+        return self._values
+
+    def indices(self):
+        """[4, cap] like paddle (columns beyond nnz() are padding)."""
+        return self.index.coords.t()
+
+    def nnz(self):
+        return int(self.index.num.item()) if self.index.num is not None else self.index.cap
+
+    def to_dense(self):
+        """[B, D, H, W, C] (sparse_resnet.py:202).  SparseResNet3D's to_dense+transpose+reshape is served in one
+        pass by `to_dense_bev`."""
+        B = self.index.batch
+        D, H, W = self.index.spatial
+        return self.to_dense_bev().view(B, self.channels, D, H, W).permute(0, 2, 3, 4, 1)
+
+    def to_dense_bev(self):
+        return _ps.sparse_to_dense_bev(self.values(), self.index.coords, self.index.batch, self.index.spatial,
+                                       num=self.index.num)
+
+
+def sparse_coo_tensor(indices, values, shape, stop_gradient=True, num=None):
+    """indices [4, nnz] (paddle layout) or [nnz, 4]; values [nnz, C]; shape [B, D, H, W, C]."""
+    values = require_cuda(values, "values", torch.float32)
+    indices = require_cuda(indices, "indices")
+    if indices.dim() != 2:
+        raise ValueError("indices must be 2-D")
+    if indices.shape[0] == 4 and indices.shape[1] != 4:
+        indices = indices.t()
+    coords = indices.to(torch.int32).contiguous()
+    cap = coords.shape[0]
+    idx = _IndexSet(coords, num, cap, int(shape[0]), [int(s) for s in shape[1:4]])
+    return SparseCooTensor(idx, values=values, channels=int(shape[4]))
+
+
+class _Pending:
+    __slots__ = ("x", "nbr", "num", "cap", "K", "cin", "cout", "weight", "scale", "shift", "residual", "relu", "precision")
+
+
+def _run(p):
+    xin = p.x.values()
+    dev = xin.device
+    out = torch.empty((p.cap, p.cout), dtype=torch.float32, device=dev)
+    res = p.residual.values() if p.residual is not None else None
+    check(lib().p3d_sparse_conv_gather_gemm(ptr(xin), ptr(p.nbr), ptr(p.num), p.cap, p.K, p.cin, p.cout,
+                                            ptr(p.weight), ptr(p.scale), ptr(p.shift), ptr(res), int(p.relu),
+                                            int(p.precision), ptr(out), stream(dev)), "sparse_conv_gather_gemm")
+    return out
+
+
+def _affine_act(x, scale, shift, residual, relu):
+    v = x.values()
+    out = torch.empty_like(v)
+    res = residual.values() if residual is not None else None
+    check(lib().p3d_sparse_affine_act(ptr(v), ptr(x.index.num), x.index.cap, x.channels, ptr(scale), ptr(shift),
+                                      ptr(res), int(relu), ptr(out), stream(v.device)), "sparse_affine_act")
+    return SparseCooTensor(x.index, values=out, channels=x.channels)
+
+
+def add(x, y):
+    """paddle.sparse.add for tensors over the same index set (sparse_resnet.py:108)."""
+    if x.index is not y.index:
+        raise NotImplementedError("sparse add over different index sets is outside the hot path")
+    p = x._pending
+    if p is not None and p.residual is None and not p.relu:
+        p.residual = y
+        return x
+    p = y._pending
+    if p is not None and p.residual is None and not p.relu:
+        p.residual = x
+        return y
+    return _affine_act(x, None, None, y, False)
+
+
+class _Layer:
+    training = False
+
+    def __call__(self, *a, **k):
+        return self.forward(*a, **k)
+
+    def eval(self):
+        return self
+
+
+class _ConvBase(_Layer):
+    subm = False
+
+    def __init__(self, in_channels, out_channels, kernel_size, stride=1, padding=0, dilation=1, groups=1,
+                 padding_mode="zeros", key=None, weight_attr=None, bias_attr=None, data_format="NDHWC"):
+        if _triple(dilation) != [1, 1, 1] or groups != 1:
+            raise NotImplementedError("dilation/groups are not used on the hot path")
+        self.in_channels, self.out_channels = int(in_channels), int(out_channels)
+        self.kernel_size, self.stride, self.padding = _triple(kernel_size), _triple(stride), _triple(padding)
+        self.key = key
+        self.weight = None  # [kD, kH, kW, Cin, Cout] fp32, Paddle's layout
+        self.bias = None if bias_attr is False else "uninit"
+        self.precision = None
+        self.out_cap = None  # strided conv: capacity of the output index set (default 4x input capacity)
+
+    def init_parameters(self, rng, device):
+        """Kaiming-uniform(a=sqrt(5)) weights and uniform(+-1/sqrt(fan_in)) bias, as
+        paddle3d.models.layers.param_init.reset_parameters (param_init.py:236-249) does for these layers."""
+        kd, kh, kw = self.kernel_size
+        fan_in = self.in_channels * kd * kh * kw
+        bound = math.sqrt(6.0 / ((1 + 5.0) * fan_in))
+        w = rng.uniform(-bound, bound, size=(kd, kh, kw, self.in_channels, self.out_channels)).astype(np.float32)
+        self.weight = torch.from_numpy(w).to(device)
+        if self.bias is not None:
+            b = rng.uniform(-1 / math.sqrt(fan_in), 1 / math.sqrt(fan_in), size=(self.out_channels,)).astype(np.float32)
+            self.bias = torch.from_numpy(b).to(device)
+        return self
+
+    def set_parameters(self, weight, bias=None):
+        self.weight = require_cuda(weight, "weight", torch.float32)
+        self.bias = require_cuda(bias, "bias", torch.float32) if bias is not None else None
+        return self
+
+    def forward(self, x):
+        if self.weight is None or isinstance(self.bias, str):
+            raise RuntimeError("conv parameters not set")
+        K = self.kernel_size[0] * self.kernel_size[1] * self.kernel_size[2]
+        p = _Pending()
+        p.x, p.K, p.cin, p.cout = x, K, self.in_channels, self.out_channels
+        p.weight, p.scale, p.shift, p.residual, p.relu = self.weight, None, self.bias, None, False
+        p.precision = self.precision if self.precision is not None else _default_precision[0]
+        if p.precision == TF32X3 and (self.in_channels % 16 or self.out_channels % 16):
+            p.precision = FP32  # the 5-channel input layer stays on the exact fp32 path
+        if self.subm:
+            index = x.index
+            p.nbr = index.subm_rulebook(self.kernel_size, self.key)
+        else:
+            src = x.index
+            dev = src.coords.device
+            cap = self.out_cap if self.out_cap is not None else 4 * src.cap
+            out_coords = torch.empty((cap, 4), dtype=torch.int32, device=dev)
+            n_out = torch.empty((4,), dtype=torch.int32, device=dev)
+            nbr = torch.empty((cap, K), dtype=torch.int32, device=dev)
+            L = lib()
+            ws = workspace(L.p3d_sparse_rulebook_workspace_bytes(src.cap, cap), dev, "rulebook")
+            check(L.p3d_sparse_rulebook_conv(ptr(src.coords), ptr(src.num), src.cap, src.batch, host_ints(src.spatial),
+                                             host_ints(self.kernel_size), host_ints(self.stride),
+                                             host_ints(self.padding), ptr(out_coords), ptr(n_out), cap, ptr(nbr),
+                                             ptr(ws), ws.numel(), stream(dev)), "sparse_rulebook_conv")
+            osp = [(src.spatial[a] + 2 * self.padding[a] - self.kernel_size[a]) // self.stride[a] + 1 for a in range(3)]
+            index = _IndexSet(out_coords, n_out, cap, src.batch, osp)
+            index.counters = n_out
+            p.nbr = nbr
+        p.num, p.cap = index.num, index.cap
+        return SparseCooTensor(index, channels=self.out_channels, pending=p)
+
+
+class SubmConv3D(_ConvBase):
+    """Outputs only at the input sites; stride forced to 1 and padding to k//2 (Paddle's
+    ResetSubmKernelSizeAndStrides)."""
+    subm = True
+
+
+class Conv3D(_ConvBase):
+    subm = False
+
+
+class BatchNorm(_Layer):
+    """paddle.sparse.nn.BatchNorm in inference mode: per-channel affine on the values."""
+
+    def __init__(self, num_features, momentum=0.9, epsilon=1e-5, weight_attr=None, bias_attr=None,
+                 data_format="NDHWC", use_global_stats=None):
+        self.num_features, self.epsilon = int(num_features), float(epsilon)
+        self.weight = self.bias = self._mean = self._variance = None
+        self._folded = None
+        self._bias_fold = {}  # conv bias tensor id -> folded shift (computed once, not per forward)
+
+    def init_parameters(self, rng, device, randomize=False):
+        c = self.num_features
+        if randomize:  # non-trivial statistics for tests
+            g, b = rng.uniform(0.5, 1.5, c), rng.uniform(-0.2, 0.2, c)
+            m, v = rng.uniform(-0.1, 0.1, c), rng.uniform(0.5, 1.5, c)
+        else:  # constant_init(weight, 1), constant_init(bias, 0), running stats (0, 1): sparse_resnet.py:177-183
+            g, b, m, v = np.ones(c), np.zeros(c), np.zeros(c), np.ones(c)
+        return self.set_parameters(*[torch.from_numpy(np.asarray(a, np.float32)).to(device) for a in (g, b, m, v)])
+
+    def set_parameters(self, weight, bias, mean, variance):
+        self.weight, self.bias, self._mean, self._variance = weight, bias, mean, variance
+        # fold once, in fp64 on the host side of the parameters (tiny): y = x*scale + shift
+        w, b, m, v = [t.double() for t in (weight, bias, mean, variance)]
+        scale = w / torch.sqrt(v + self.epsilon)
+        self._folded = (scale.float().contiguous(), (b - m * scale).float().contiguous())
+        return self
+
+    def forward(self, x):
+        scale, shift = self._folded
+        p = x._pending
+        if p is not None and p.scale is None and p.residual is None and not p.relu:
+            # (conv + bias) * scale + shift  ==  conv * scale + (bias * scale + shift)
+            if p.shift is not None:
+                key = p.shift.data_ptr()
+                if key not in self._bias_fold:
+                    self._bias_fold[key] = (p.shift.double() * scale.double() + shift.double()).float().contiguous()
+                shift = self._bias_fold[key]
+            p.shift = shift
+            p.scale = scale
+            return x
+        return _affine_act(x, scale, shift, None, False)
+
+
+class ReLU(_Layer):
+    def forward(self, x):
+        p = x._pending
+        if p is not None:
+            p.relu = True
+            return x
+        return _affine_act(x, None, None, None, True)
+
+
+class _NN:
+    SubmConv3D, Conv3D, BatchNorm, ReLU = SubmConv3D, Conv3D, BatchNorm, ReLU
+
+
+nn = _NN()

@@ -1,0 +1,103 @@
+"""CPU suite: the oracle against the reference's golden vectors / the reference itself; no GPU."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from conftest import ROOT, golden
+from paddle3d_b200 import synth
+
+VOX = sorted(os.path.basename(p) for p in glob.glob(os.path.join(ROOT, "tests", "golden", "voxelize_*.npz")))
+
+
+@pytest.mark.parametrize("name", VOX)
+def test_voxelize_oracle_matches_reference_golden(oracle_mod, name):
+    g = golden(name)
+    v, c, n, nv = oracle_mod.hard_voxelize(g["points"], g["voxel_size"], g["point_cloud_range"], int(g["max_points"]),
+                                           int(g["max_voxels"]))
+    assert int(nv[0]) == int(g["num_voxels"][0])
+    assert np.array_equal(c, g["coords"])
+    assert np.array_equal(n, g["num_points_per_voxel"])
+    assert np.array_equal(v, g["voxels"])
+
+
+def test_iou_oracle_matches_reference_golden(oracle_mod):
+    g = golden("iou_bev.npz")
+    iou = oracle_mod.boxes_iou_bev(g["boxes_a"], g["boxes_b"])
+    assert np.array_equal(iou, g["iou"])  # bit exact: same fp32 operations, no FMA on either side
+    assert (g["iou"] > 0.05).sum() > 100
+
+
+@pytest.mark.parametrize("cfg,seed", [(synth.C1, 3), (synth.C2, 4)])
+def test_voxelize_oracle_matches_reference_library(oracle_mod, cfg, seed):
+    if oracle_mod.ref_lib("cpu") is None:
+        pytest.skip("oracle/_ref not built (no /root/reference here)")
+    pts = synth.lidar_cloud(cfg, seed, num_points=min(cfg["num_points"], 20000))
+    a = oracle_mod.hard_voxelize(pts, cfg["voxel_size"], cfg["point_cloud_range"], 5, 3000)
+    b = oracle_mod.ref_hard_voxelize_cpu(pts, cfg["voxel_size"], cfg["point_cloud_range"], 5, 3000)
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y)
+
+
+def test_iou_oracle_matches_reference_library(oracle_mod):
+    if oracle_mod.ref_lib("cpu") is None:
+        pytest.skip("oracle/_ref not built")
+    a = synth.random_boxes(200, 21)
+    assert np.array_equal(oracle_mod.boxes_iou_bev(a, a), oracle_mod.ref_boxes_iou_bev_cpu(a, a))
+
+
+def test_voxelize_edge_cases(oracle_mod):
+    cfg = synth.C1
+    empty = np.zeros((0, 4), np.float32)
+    v, c, n, nv = oracle_mod.hard_voxelize(empty, cfg["voxel_size"], cfg["point_cloud_range"], 4, 16)
+    assert nv[0] == 0 and not v.any() and not c.any() and not n.any()
+    outside = np.full((10, 4), 1e6, np.float32)
+    assert oracle_mod.hard_voxelize(outside, cfg["voxel_size"], cfg["point_cloud_range"], 4, 16)[3][0] == 0
+    # point exactly on the upper boundary is dropped, on the lower boundary is kept (voxelize_op.cc:47-55)
+    pcr = cfg["point_cloud_range"]
+    pts = np.array([[pcr[0], pcr[1], pcr[2], 1.0], [pcr[3], pcr[4], pcr[5], 1.0]], np.float32)
+    v, c, n, nv = oracle_mod.hard_voxelize(pts, cfg["voxel_size"], pcr, 4, 16)
+    assert nv[0] == 1 and list(c[0]) == [0, 0, 0]
+
+
+def test_nms_oracle_properties(oracle_mod):
+    b = synth.random_boxes(300, 5)
+    keep, nk = oracle_mod.nms(b, 0.2)
+    kept = b[keep[:nk]]
+    iou = oracle_mod.boxes_iou_bev(kept, kept)
+    np.fill_diagonal(iou, 0)
+    assert (iou <= 0.2).all()  # survivors do not suppress each other
+    assert keep[0] == 0  # best box always survives
+    # idempotence: NMS of the survivors keeps all of them
+    _, nk2 = oracle_mod.nms(kept, 0.2)
+    assert nk2 == nk
+
+
+def test_sparse_conv_oracle_vs_torch_dense(oracle_mod):
+    """The sparse-conv restatement against a dense fp64 conv3d over the active-site mask."""
+    import torch
+    rng = np.random.default_rng(0)
+    B, D, H, W, Cin, Cout = 2, 7, 10, 9, 5, 6
+    occ = rng.random((B, D, H, W)) < 0.15
+    coords = np.argwhere(occ).astype(np.int32)
+    feats = rng.normal(size=(len(coords), Cin)).astype(np.float32)
+    dense = np.zeros((B, Cin, D, H, W))
+    dense[coords[:, 0], :, coords[:, 1], coords[:, 2], coords[:, 3]] = feats
+    for subm, ks, st, pd in [(True, (3, 3, 3), (1, 1, 1), (1, 1, 1)), (False, (3, 3, 3), (2, 2, 2), (1, 1, 1)),
+                             (False, (3, 3, 3), (2, 2, 2), (0, 1, 1)), (False, (3, 1, 1), (2, 1, 1), (0, 0, 0))]:
+        w = rng.normal(size=ks + (Cin, Cout)).astype(np.float32)
+        oc, of, osp, pairs = oracle_mod.sparse_conv3d(coords, feats, B, (D, H, W), w, st, pd, subm)
+        wt = torch.from_numpy(w.astype(np.float64)).permute(4, 3, 0, 1, 2)
+        ref = torch.nn.functional.conv3d(torch.from_numpy(dense), wt, stride=st, padding=(pd if not subm else (1, 1, 1))).numpy()
+        act = torch.nn.functional.conv3d(torch.from_numpy(occ[:, None].astype(np.float64)),
+                                         torch.ones((1, 1) + ks, dtype=torch.float64), stride=st,
+                                         padding=(pd if not subm else (1, 1, 1))).numpy()[:, 0] > 0
+        if subm:
+            act = occ
+        assert list(ref.shape[2:]) == osp
+        assert len(oc) == act.sum()
+        got = np.zeros_like(ref)
+        got[oc[:, 0], :, oc[:, 1], oc[:, 2], oc[:, 3]] = of
+        np.testing.assert_allclose(got, ref * act[:, None], rtol=1e-5, atol=1e-5)
+        assert pairs > 0
