@@ -1,0 +1,365 @@
+#!/usr/bin/env python
+"""bench.py — CenterPoint hot-path frames/s on B200 (driver contract, see the task's Measurement rules).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            this repo's CUDA path
+  python bench.py --impl reference [--steps K] [--warmup W]      the reference's CPU arm on the host cores
+
+A step = one pass of the hot path over one synthetic nuScenes-shaped frame (config C3: 300k x 5 points,
+0.075 m voxels, 1440 x 1440 x 40 grid, max 160000 voxels):
+    voxelize+VoxelMean -> SparseResNet3D (21 sparse convs) -> dense BEV -> centerpoint_postprocess.
+The dense 2-D RPN/head between the BEV tensor and the postprocess is not built
+yet, so the postprocess consumes resident synthetic head tensors; `config.workload` says so.
+
+`value`  : frames/s with the frame's points already resident in HBM (CUDA-graph replay per frame).
+`e2e`    : frames/s through the public API CenterPointHotPath.infer(): pinned-host points -> H2D ->
+           graph -> D2H of boxes/scores/labels/counts, every step.
+`roofline`: dominant kernel, timed live with CUDA events on the launching stream.
+N > 1: frame-parallel replicas, one process per GPU (torchrun), weights broadcast once over NCCL,
+no per-frame collective; value = total frames / max-over-ranks time ("weak" scaling).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "CenterPoint frames/sec @300k pts, 0.075m voxel, 1440x1440x40 grid"
+UNIT = "frames/s"
+WORKLOAD = ("C3 centerpoint_voxel_0075 hot path: hard_voxelize+VoxelMean -> SparseResNet3D(21 sparse convs) -> "
+            "dense BEV [1,256,180,180] -> centerpoint_postprocess(6 tasks, synthetic head tensors); "
+            "dense 2-D RPN/head (SURVEY §8f-1) not included")
+POOL = 32  # distinct frames cycled through: 32 x 6 MB = 192 MB of inputs > 126 MB L2
+
+
+def frame_pool(cfg, n_frames, seed0=0, base=4):
+    """`base` ray-cast lidar clouds, expanded to n_frames by a seeded yaw rotation + jitter (cheap, distinct)."""
+    from paddle3d_b200 import synth
+    bases = [synth.lidar_cloud(cfg, seed0 + i) for i in range(base)]
+    out = []
+    for f in range(n_frames):
+        rng = np.random.default_rng(1000 + seed0 + f)
+        p = bases[f % base].copy()
+        if f >= base:
+            a = rng.uniform(0, 2 * np.pi)
+            c, s = np.cos(a), np.sin(a)
+            xy = p[:, :2] @ np.array([[c, -s], [s, c]], np.float32)
+            p[:, :2] = xy + rng.normal(0, 0.01, size=xy.shape).astype(np.float32)
+            rng.shuffle(p, axis=0)
+        out.append(np.ascontiguousarray(p, dtype=np.float32))
+    return out
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag, self.proc = index, [], False, None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.samples.append([x.strip() for x in line.split(",")])
+                if self.stop_flag:
+                    break
+        except Exception:
+            pass
+
+    def finish(self):
+        self.stop_flag = True
+        if self.proc is not None:
+            try:
+                self.proc.terminate()
+            except Exception:
+                pass
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            try:
+                sm.append(float(s[0]))
+                mx = max(mx, float(s[1]))
+                for nme, v in zip(names, s[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nme)
+            except Exception:
+                continue
+        load = sorted(sm)[len(sm) // 2:] if sm else []
+        return {"sm_mhz": (sorted(load)[len(load) // 2] if load else None), "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return d.get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
+
+
+def run_reference(args):
+    """CPU arm: the reference's own CPU voxelizer (oracle/_ref, when built) + the oracle port for the stages
+    the reference only implements on the GPU / inside PaddlePaddle.  One step = one full frame."""
+    import torch  # noqa: F401  (weights are generated with the same seeded code path as the CUDA arm)
+    from paddle3d_b200 import synth
+    from paddle3d_b200.cpu_reference import CpuFrame
+    from paddle3d_b200.layers import SparseResNet3D
+    from paddle3d_b200.pipeline import CenterPointHotPath
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle
+    cfg = synth.C3
+
+    class _W:
+        pass
+    w = _W()
+    w.net = SparseResNet3D(cfg["point_dim"], cfg["voxel_size"], cfg["point_cloud_range"]).init_weight(seed=0, device="cpu")
+    weights = CenterPointHotPath.export_weights_numpy(w)
+    head = synth.centerpoint_head_outputs(0)
+    cf = CpuFrame(cfg, weights, head, synth.CENTERPOINT_TEST_CFG, synth.label_offsets())
+    frames = frame_pool(cfg, 4, base=2)
+    for i in range(args.warmup):
+        cf.run(frames[i % len(frames)])
+    t0 = time.perf_counter()
+    stages = {}
+    for i in range(args.steps):
+        r = cf.run(frames[i % len(frames)])
+        for k, v in r["times"].items():
+            stages[k] = stages.get(k, 0.0) + v
+    dt = time.perf_counter() - t0
+    fps = args.steps / dt
+    cores = oracle.num_threads()
+    kind = "port"
+    sample = ("%d full C3 frames; voxelize = %s, voxel_mean/sparse conv/to_dense/postprocess = oracle port "
+              "(OpenMP, %d threads; the reference has no CPU implementation of them)" %
+              (args.steps, "reference hard_voxelize_cpu compiled unmodified (oracle/_ref)" if cf.use_ref else "oracle port", cores))
+    line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD},
+            "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+            "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "stage_ms": {k: 1e3 * v / args.steps for k, v in stages.items()}, "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def kernel_time_ms(fn, stream, iters):
+    """CUDA-event time of `fn` on `stream`, averaged over iters (after one warm call)."""
+    import torch
+    with torch.cuda.stream(stream):
+        fn()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record(stream)
+        for _ in range(iters):
+            fn()
+        e.record(stream)
+    e.synchronize()
+    return s.elapsed_time(e) / iters
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--precision", default="fp32", choices=["fp32", "tf32x3"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        args.steps = max(1, args.steps)
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from paddle3d_b200 import synth
+    from paddle3d_b200.ops import sparse_nn as sp
+    from paddle3d_b200.ops import voxelize as vox
+    from paddle3d_b200.pipeline import CenterPointHotPath
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback exists); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    cfg = synth.C3
+    precision = sp.TF32X3 if args.precision == "tf32x3" else sp.FP32
+    pipe = CenterPointHotPath(cfg, dev, precision=precision, seed=0)
+    if world > 1:  # weights only: one broadcast over NVLink at start, no per-frame collective
+        for l in pipe.net.all_layers():
+            for name in ("weight", "bias", "_mean", "_variance"):
+                t = getattr(l, name, None)
+                if isinstance(t, torch.Tensor):
+                    dist.broadcast(t, 0)
+        for l in pipe.net.all_layers():
+            if isinstance(l, sp.BatchNorm):
+                l._bias_fold.clear()
+                l.set_parameters(l.weight, l.bias, l._mean, l._variance)
+    # frames: rank r owns frames r, r + world, ... of the sweep (frame-parallel sharding)
+    frames = frame_pool(cfg, POOL, seed0=rank * 100)
+    dev_frames = [torch.from_numpy(f).to(dev) for f in frames]
+    host_frames = [torch.from_numpy(f).pin_memory() for f in frames]
+    pipe.points.copy_(dev_frames[0])
+    pipe.capture()
+    graph_nodes = None
+    st = pipe.stream
+
+    def step_resident(i):
+        with torch.cuda.stream(st):
+            pipe.points.copy_(dev_frames[i % POOL], non_blocking=True)  # D2D: the frame is already in HBM
+            pipe.graph.replay()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step_resident(i)
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    time.sleep(0.3)
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t0 = time.perf_counter()
+    s.record(st)
+    for i in range(args.steps):
+        step_resident(i)
+    e.record(st)
+    barrier()
+    wall = time.perf_counter() - t0
+    dev_ms = s.elapsed_time(e)
+    # ---- e2e through the public API (host in, host out), same K
+    for i in range(3):
+        pipe.infer(host_frames[i % POOL])
+    barrier()
+    t1 = time.perf_counter()
+    for i in range(args.steps):
+        pipe.infer(host_frames[i % POOL])
+    barrier()
+    e2e_s = time.perf_counter() - t1
+    clocks = sampler.finish()
+
+    tt = torch.tensor([dev_ms, e2e_s * 1e3, wall * 1e3], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms, wall_ms = [float(x) for x in tt.cpu()]
+    total_frames = args.steps * world
+    value = total_frames / (dev_ms * 1e-3)
+    e2e_value = total_frames / (e2e_ms * 1e-3)
+
+    # ---- roofline of the dominant kernels, timed live (events on the launching stream), rank 0 only
+    extra = {}
+    if rank == 0:
+        hbm_peak, peak_src = peaks()
+        N, F, P, V = pipe.n, pipe.F, cfg["max_points"], cfg["max_voxels"]
+        pts = dev_frames[0]
+        # hard_voxelize op (reference API, zero-padded outputs): 4NF + 4VPF + 12V + 4V + 4 bytes
+        vox_bytes = 4 * N * F + 4 * V * P * F + 12 * V + 4 * V + 4
+        ms_vox = kernel_time_ms(lambda: vox.hard_voxelize(pts, cfg["voxel_size"], cfg["point_cloud_range"], P, V), st, 20)
+        # per-stage device times of the captured frame (eager re-run with events)
+        stage = {}
+        with torch.cuda.stream(st):
+            pipe.points.copy_(dev_frames[0])
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+            ev[0].record(st)
+            mean, coors, npv, nv = vox.voxelize_mean(pipe.points, cfg["voxel_size"], cfg["point_cloud_range"], P, V, 0)
+            ev[1].record(st)
+            x, _ = pipe.net.forward_sparse(mean, coors, 1, num=nv)
+            x.values()
+            ev[2].record(st)
+            x.to_dense_bev()
+            ev[3].record(st)
+            from paddle3d_b200.ops import centerpoint_postprocess as cpp
+            h, tc = pipe.head, pipe.test_cfg
+            cpp.centerpoint_postprocess_device(h["hm"], h["reg"], h["height"], h["dim"], h["vel"], h["rot"],
+                                               cfg["voxel_size"][:2], cfg["point_cloud_range"],
+                                               tc["post_center_limit_range"], pipe.label_off, tc["down_ratio"],
+                                               tc["score_threshold"], tc["nms_iou_threshold"], tc["nms_pre_max_size"],
+                                               tc["nms_post_max_size"], True)
+            ev[4].record(st)
+        ev[4].synchronize()
+        names = ["voxelize_mean", "sparse_backbone(eager launches)", "to_dense_bev", "postprocess"]
+        for k in range(4):
+            stage[names[k]] = ev[k].elapsed_time(ev[k + 1])
+        nvox = int(nv.item())
+        extra["stage_ms_eager"] = stage
+        extra["num_voxels_frame0"] = nvox
+        roof = {"bound": "hbm", "kernel": "hard_voxelize op (5 launches; vox_write_kernel dominates)",
+                "achieved": vox_bytes / (ms_vox * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                "frac": vox_bytes / (ms_vox * 1e-3) / 1e9 / hbm_peak, "traffic": None,
+                "algorithmic_bytes": vox_bytes, "ms": ms_vox, "peak_source": peak_src}
+        extra["roofline"] = roof
+        # CPU baseline on a bounded sample: one full frame through the oracle port
+        if not args.no_cpu_baseline:
+            from paddle3d_b200.cpu_reference import CpuFrame
+            import oracle
+            cf = CpuFrame(cfg, pipe.export_weights_numpy(), pipe.head_host, pipe.test_cfg, pipe.label_off)
+            t2 = time.perf_counter()
+            r = cf.run(frames[0])
+            cpu_s = time.perf_counter() - t2
+            extra["cpu_baseline"] = {"value": 1.0 / cpu_s, "unit": UNIT, "cores": oracle.num_threads(), "kind": "port",
+                                     "sample": "1 full C3 frame (frame 0 of the pool); voxelize = %s; other stages = "
+                                               "oracle port with OpenMP" % ("reference hard_voxelize_cpu (oracle/_ref)"
+                                                                            if cf.use_ref else "oracle port"),
+                                     "stage_s": r["times"]}
+            # cross-check while we are here: GPU frame vs CPU frame on the same input
+            got = pipe.infer(host_frames[0])
+            extra["frame0_check"] = {"labels_equal": bool(np.array_equal(got[2].numpy(), r["labels"])),
+                                     "num_voxels_equal": nvox == r["num_voxels"]}
+
+    if rank == 0:
+        h2d, d2h = pipe.bytes_per_frame()
+        n_launch = None
+        try:
+            n_launch = len(pipe.graph.debug_dump) if False else None
+        except Exception:
+            pass
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32" if precision == sp.FP32 else "tf32x3(f32 accum)",
+                "data": "synthetic", "config": {"workload": WORKLOAD, "frames_in_pool": POOL,
+                                                "l2": "input pool 192 MB > 126 MB L2; no explicit flush",
+                                                "parallelism": "frame-parallel x%d (replicas, NCCL weight broadcast only)" % world,
+                                                "precision": args.precision},
+                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                "gpu_launches": pipe_launch_count(pipe) * args.steps, "clocks": clocks, "wall_ms_per_step": wall_ms / args.steps}
+        line.update(extra)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def pipe_launch_count(pipe):
+    """Kernels of ours per frame: voxelize front end 5, rulebooks (1 subm x 3 launches... counted explicitly)."""
+    vox_k = 5                      # init, insert, rank, slots, mean
+    rb = 2 + 3 * 2 + 4 * 4 + 0     # res0 subm (insert+nbr) ; res1-3 subm (insert+nbr) ; 4 strided (insert, outputs, finish, nbr)
+    conv = 21
+    dense = 2                      # scat_map + scat_write
+    post = 5
+    return vox_k + rb + conv + dense + post
+
+
+if __name__ == "__main__":
+    main()

@@ -153,7 +153,8 @@ int p3d_centerpoint_postprocess(int num_tasks, const float *const *hm, const int
  *                              nbr[o][k] = input row at o*stride - pad + k or -1.
  *   n_in_dev / n_out_dev are device scalars so the whole backbone runs without a host sync.
  *   n_out_dev[0] = number of output sites (clamped to out_cap), n_out_dev[1] = 1 if sites were
- *   dropped because out_cap was too small, n_out_dev[2] = unclamped count, n_out_dev[3] reserved.
+ *   dropped because out_cap was too small, n_out_dev[2] = unclamped count (a lower bound once the
+ *   dedup table itself is full), n_out_dev[3] = internal table-full flag.
  * ------------------------------------------------------------------------------------------- */
 size_t p3d_sparse_rulebook_workspace_bytes(int64_t n_in_cap, int64_t n_out_cap);
 int p3d_sparse_rulebook_subm(const int32_t *coords, const int32_t *n_in_dev, int64_t n_in_cap, int batch,

@@ -138,7 +138,11 @@ __global__ void __launch_bounds__(256) rb_outputs_kernel(const int32_t *__restri
   if (oz >= d.oD || oy >= d.oH || ox >= d.oW) return;
   const uint32_t key = lin(c.x, oz, oy, ox, d.oD, d.oH, d.oW);
   uint32_t h = hash32(key) >> shift;
-  while (true) {
+  for (uint32_t probes = 0;; ++probes) {
+    if (probes > mask) {  // table full (far more sites than out_cap): cannot dedupe any more, flag overflow
+      n_out_dev[3] = 1;
+      return;
+    }
     unsigned long long cur = tab_out[h];
     if (cur == kEmpty) {
       // claim the slot with a provisional row id; the winner numbers the site
@@ -161,7 +165,7 @@ __global__ void __launch_bounds__(256) rb_outputs_kernel(const int32_t *__restri
 __global__ void rb_finish_kernel(int32_t *n_out_dev, int out_cap) {
   const int raw = n_out_dev[2];
   n_out_dev[0] = raw < out_cap ? raw : out_cap;
-  n_out_dev[1] = raw > out_cap ? 1 : 0;
+  n_out_dev[1] = (raw > out_cap || n_out_dev[3]) ? 1 : 0;
 }
 
 // ------------------------------------------------------------------ fp32 gather-GEMM

@@ -82,9 +82,13 @@ __global__ void vox_init_kernel(uint4 *table16, size_t n_table16, uint4 *desc16,
 // ---------------------------------------------------------------- K1
 __device__ __forceinline__ int cell_of(const float *__restrict__ pt, const VoxGeom &g) {
   // fp32 subtract, IEEE fp32 divide, floor — exactly voxelize_op.cc:37-45
-  const int cx = static_cast<int>(floorf(__fdiv_rn(__fsub_rn(pt[0], g.min_x), g.vs_x)));
-  const int cy = static_cast<int>(floorf(__fdiv_rn(__fsub_rn(pt[1], g.min_y), g.vs_y)));
-  const int cz = static_cast<int>(floorf(__fdiv_rn(__fsub_rn(pt[2], g.min_z), g.vs_z)));
+  const float fx = floorf(__fdiv_rn(__fsub_rn(pt[0], g.min_x), g.vs_x));
+  const float fy = floorf(__fdiv_rn(__fsub_rn(pt[1], g.min_y), g.vs_y));
+  const float fz = floorf(__fdiv_rn(__fsub_rn(pt[2], g.min_z), g.vs_z));
+  // The reference CPU kernel converts with an x86 cvttss2si: NaN (and anything outside int range) becomes
+  // INT_MIN and is dropped by the `< 0` test.  CUDA's float->int turns NaN into 0, so reject it explicitly.
+  if (!(fx == fx) || !(fy == fy) || !(fz == fz)) return -1;
+  const int cx = static_cast<int>(fx), cy = static_cast<int>(fy), cz = static_cast<int>(fz);
   if (cx < 0 || cx >= g.gx || cy < 0 || cy >= g.gy || cz < 0 || cz >= g.gz) return -1;
   return (cz * g.gy + cy) * g.gx + cx;
 }

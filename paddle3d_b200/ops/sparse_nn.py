@@ -83,7 +83,7 @@ class SparseCooTensor:
         return self.index.coords.t()
 
     def nnz(self):
-        return int(self.index.num.item()) if self.index.num is not None else self.index.cap
+        return int(self.index.num[0].item()) if self.index.num is not None else self.index.cap
 
     def to_dense(self):
         """[B, D, H, W, C] (sparse_resnet.py:202).  SparseResNet3D's to_dense+transpose+reshape is served in one

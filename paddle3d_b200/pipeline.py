@@ -1,0 +1,120 @@
+"""CenterPoint-voxel hot-path frame on one B200: the public API a user calls (bench.py `e2e`).
+
+    voxelize (+ VoxelMean fused)  ->  SparseResNet3D (21 sparse convs)  ->  dense BEV [1,256,180,180]
+    -> [dense 2-D RPN + CenterHead: SURVEY.md §8f rank 1, NOT built yet: head tensors are synthetic] ->
+    centerpoint_postprocess -> boxes
+
+Everything between the H2D copy of the points and the D2H copy of the boxes is captured once in a
+CUDA graph (data-dependent row counts live in device scalars, buffers are sized by capacity), so a
+frame is: cudaMemcpyAsync H2D, one graph launch, cudaMemcpyAsync D2H.
+Call sites mirrored: CenterPoint.extract_feat (centerpoint.py:126-138) and
+CenterHead.predict_by_custom_op (center_head.py:294-339).
+"""
+import numpy as np
+import torch
+
+from . import synth
+from .layers import SparseResNet3D
+from .ops import centerpoint_postprocess as cpp
+from .ops import sparse_nn as sp
+from .ops import voxelize as vox
+
+
+class CenterPointHotPath:
+    def __init__(self, cfg=None, device="cuda:0", precision=sp.FP32, seed=0, num_points=None, level_caps=None,
+                 head_seed=0):
+        self.cfg = dict(cfg or synth.C3)
+        self.device = torch.device(device)
+        self.n = int(num_points or self.cfg["num_points"])
+        self.F = self.cfg["point_dim"]
+        self.test_cfg = dict(synth.CENTERPOINT_TEST_CFG)
+        self.label_off = synth.label_offsets()
+        self.net = SparseResNet3D(self.F, self.cfg["voxel_size"], self.cfg["point_cloud_range"])
+        self.net.init_weight(seed=seed, device=self.device).set_precision(precision)
+        V = self.cfg["max_voxels"]
+        self.net.set_level_caps(level_caps or [3 * V, 3 * V, 2 * V, V])
+        h = synth.centerpoint_head_outputs(head_seed)
+        self.head_host = h
+        self.head = {k: [torch.from_numpy(x).to(self.device) for x in v] for k, v in h.items()}
+        self.points = torch.zeros((self.n, self.F), dtype=torch.float32, device=self.device)  # static input
+        self.graph = None
+        self.out = None
+        self.stream = torch.cuda.Stream(self.device)
+        rows = len(self.label_off) * self.test_cfg["nms_post_max_size"]
+        self.h_boxes = torch.empty((rows, 9), dtype=torch.float32).pin_memory()
+        self.h_scores = torch.empty((rows,), dtype=torch.float32).pin_memory()
+        self.h_labels = torch.empty((rows,), dtype=torch.int64).pin_memory()
+        self.h_counts = torch.empty((len(self.label_off) + 1,), dtype=torch.int32).pin_memory()
+
+    # ---- one frame, enqueued on the current stream, device in / device out
+    def forward_device(self):
+        cfg, tc = self.cfg, self.test_cfg
+        mean, coors, npv, nv = vox.voxelize_mean(self.points, cfg["voxel_size"], cfg["point_cloud_range"],
+                                                 cfg["max_points"], cfg["max_voxels"], 0)
+        bev = self.net(mean, coors, 1, num=nv)
+        h = self.head
+        boxes, scores, labels, counts = cpp.centerpoint_postprocess_device(
+            h["hm"], h["reg"], h["height"], h["dim"], h["vel"], h["rot"], cfg["voxel_size"][:2],
+            cfg["point_cloud_range"], tc["post_center_limit_range"], self.label_off, tc["down_ratio"],
+            tc["score_threshold"], tc["nms_iou_threshold"], tc["nms_pre_max_size"], tc["nms_post_max_size"], True)
+        return dict(bev=bev, boxes=boxes, scores=scores, labels=labels, counts=counts, num_voxels=nv, coors=coors,
+                    mean=mean)
+
+    def capture(self, warmup=2):
+        """Warm up (sizes the workspaces) on the side stream, then capture the frame into a CUDA graph."""
+        with torch.cuda.stream(self.stream):
+            for _ in range(warmup):
+                self.out = self.forward_device()
+            self.stream.synchronize()
+            self.graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self.graph, stream=self.stream):
+                self.out = self.forward_device()
+        self.stream.synchronize()
+        return self
+
+    def launch(self):
+        """Replay the captured frame on the pipeline stream (inputs already in self.points)."""
+        with torch.cuda.stream(self.stream):
+            self.graph.replay()
+
+    # ---- public end-to-end call: host points in, host boxes out
+    def infer(self, points_host):
+        """points_host: pinned [n, F] fp32 tensor.  Returns (boxes [K,9], scores [K], labels [K]) on the host."""
+        with torch.cuda.stream(self.stream):
+            self.points.copy_(points_host, non_blocking=True)
+            if self.graph is not None:
+                self.graph.replay()
+            else:
+                self.out = self.forward_device()
+            o = self.out
+            self.h_counts.copy_(o["counts"], non_blocking=True)
+            self.h_boxes.copy_(o["boxes"], non_blocking=True)
+            self.h_scores.copy_(o["scores"], non_blocking=True)
+            self.h_labels.copy_(o["labels"], non_blocking=True)
+        self.stream.synchronize()
+        k = int(self.h_counts[-1])
+        return self.h_boxes[:k], self.h_scores[:k], self.h_labels[:k]
+
+    def bytes_per_frame(self):
+        h2d = self.n * self.F * 4
+        d2h = self.h_boxes.numel() * 4 + self.h_scores.numel() * 4 + self.h_labels.numel() * 8 + self.h_counts.numel() * 4
+        return h2d, d2h
+
+    def export_weights_numpy(self):
+        """Weights as plain numpy dicts for the CPU arm (cpu_reference.CpuFrame)."""
+        def conv(l):
+            return dict(weight=l.weight.cpu().numpy(), bias=None if l.bias is None else l.bias.cpu().numpy(),
+                        stride=l.stride, padding=l.padding)
+
+        def bn(l):
+            return dict(gamma=l.weight.cpu().numpy(), beta=l.bias.cpu().numpy(), mean=l._mean.cpu().numpy(),
+                        var=l._variance.cpu().numpy(), eps=l.epsilon)
+
+        def block(b):
+            return dict(conv1=conv(b.conv1), bn1=bn(b.bn1), conv2=conv(b.conv2), bn2=bn(b.bn2))
+
+        n = self.net
+        return dict(conv_input=dict(conv=conv(n.conv_input[0]), bn=bn(n.conv_input[1])),
+                    blocks0=[block(b) for b in n.blocks0],
+                    stages=[dict(down=dict(conv=conv(d[0]), bn=bn(d[1])), blocks=[block(b) for b in bl]) for d, bl in n.stages],
+                    extra=dict(conv=conv(n.extra_conv[0]), bn=bn(n.extra_conv[1])))

@@ -1,0 +1,140 @@
+"""GPU parity: sparse conv (rulebook + gather-GEMM) and SparseResNet3D through the C ABI vs the oracle.
+Tolerance: 1e-4 relative (fp32), BASELINE.json north_star.  PARITY UNPINNED by the reference (the
+arithmetic is PaddlePaddle's); the oracle restatement is itself checked against dense fp64 conv3d in
+tests/test_oracle.py."""
+import numpy as np
+import pytest
+
+from paddle3d_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _t(cuda, a):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(a)).to(cuda)
+
+
+def _dense(coords, feats, B, sp):
+    out = np.zeros((B,) + tuple(sp) + (feats.shape[1],), np.float32)
+    out[coords[:, 0], coords[:, 1], coords[:, 2], coords[:, 3]] = feats
+    return out
+
+
+def _rand_sites(rng, B, D, H, W, p):
+    occ = rng.random((B, D, H, W)) < p
+    c = np.argwhere(occ).astype(np.int32)
+    rng.shuffle(c, axis=0)
+    return c
+
+
+@pytest.mark.parametrize("precision", [0])
+@pytest.mark.parametrize("subm,ks,st,pd,cin,cout", [
+    (True, 3, 1, 1, 5, 16), (True, 3, 1, 1, 16, 16), (True, 3, 1, 1, 64, 64), (True, 3, 1, 1, 128, 128),
+    (False, 3, 2, 1, 16, 32), (False, 3, 2, [0, 1, 1], 64, 128), (False, (3, 1, 1), (2, 1, 1), 0, 128, 128),
+    (True, 3, 1, 1, 7, 9),
+])
+def test_single_conv(cuda, oracle_mod, precision, subm, ks, st, pd, cin, cout):
+    import torch
+    from paddle3d_b200.ops import sparse_nn as sp
+    rng = np.random.default_rng(cin * 131 + cout)
+    B, D, H, W = 2, 11, 40, 37
+    coords = _rand_sites(rng, B, D, H, W, 0.08)
+    feats = rng.normal(size=(len(coords), cin)).astype(np.float32)
+    cls = sp.SubmConv3D if subm else sp.Conv3D
+    conv = cls(cin, cout, ks, st, padding=pd, bias_attr=True)
+    conv.init_parameters(rng, cuda)
+    conv.precision = precision
+    bn = sp.BatchNorm(cout, epsilon=1e-3).init_parameters(rng, cuda, randomize=True)
+    x = sp.sparse_coo_tensor(_t(cuda, coords).t(), _t(cuda, feats), [B, D, H, W, cin])
+    y = sp.ReLU()(bn(conv(x)))
+    vals = y.values()
+    n = y.nnz()
+    got = _dense(y.index.coords.cpu().numpy()[:n], vals.cpu().numpy()[:n], B, y.index.spatial)
+    w = conv.weight.cpu().numpy()
+    oc, of, osp, pairs = oracle_mod.sparse_conv3d(coords, feats, B, (D, H, W), w, conv.stride, conv.padding, subm)
+    of = of + conv.bias.cpu().numpy()
+    of = oracle_mod.bn_relu(of, bn.weight.cpu().numpy(), bn.bias.cpu().numpy(), bn._mean.cpu().numpy(),
+                            bn._variance.cpu().numpy(), 1e-3, relu=True)
+    assert n == len(oc) and osp == y.index.spatial
+    want = _dense(oc, of, B, osp)
+    np.testing.assert_allclose(got, want, rtol=1e-4, atol=1e-4 * np.abs(want).max())
+    if not subm:
+        assert int(y.index.counters[1].item()) == 0  # no overflow
+    # to_dense_bev == reference to_dense + transpose + reshape
+    bev = y.to_dense_bev().cpu().numpy()
+    want_bev = np.transpose(want, (0, 4, 1, 2, 3)).reshape(B, cout * osp[0], osp[1], osp[2])
+    np.testing.assert_allclose(bev, want_bev, rtol=1e-4, atol=1e-4 * np.abs(want).max())
+
+
+def test_strided_overflow_is_flagged(cuda):
+    from paddle3d_b200.ops import sparse_nn as sp
+    rng = np.random.default_rng(0)
+    coords = _rand_sites(rng, 1, 9, 30, 30, 0.2)
+    x = sp.sparse_coo_tensor(_t(cuda, coords).t(), _t(cuda, rng.normal(size=(len(coords), 16)).astype(np.float32)), [1, 9, 30, 30, 16])
+    conv = sp.Conv3D(16, 16, 3, 2, padding=1, bias_attr=False).init_parameters(rng, cuda)
+    conv.out_cap = 50
+    y = conv(x)
+    y.values()
+    c = y.index.counters.cpu().numpy()
+    assert c[0] == 50 and c[1] == 1 and c[2] > 50 and c[2] <= 2048
+
+
+def _oracle_resnet(oracle_mod, net, coords, feats, B):
+    """SparseResNet3D.forward (sparse_resnet.py:185-206) composed from oracle pieces."""
+    def conv(l, c, f, sp, subm):
+        w = l.weight.cpu().numpy()
+        oc, of, osp, pairs = oracle_mod.sparse_conv3d(c, f, B, sp, w, l.stride, l.padding, subm)
+        if l.bias is not None:
+            of = of + l.bias.cpu().numpy()
+        return oc, of, osp, pairs
+
+    def bn(l, f, relu, residual=None):
+        return oracle_mod.bn_relu(f, l.weight.cpu().numpy(), l.bias.cpu().numpy(), l._mean.cpu().numpy(),
+                                  l._variance.cpu().numpy(), l.epsilon, relu=relu, residual=residual)
+
+    def block(b, c, f, sp):
+        _, o, _, p1 = conv(b.conv1, c, f, sp, True)
+        o = bn(b.bn1, o, True)
+        _, o, _, p2 = conv(b.conv2, c, o, sp, True)
+        return bn(b.bn2, o, True, residual=f), p1 + p2
+
+    sp_ = net.sparse_shape
+    pairs = []
+    c, f, _, p = conv(net.conv_input[0], coords, feats, sp_, True)
+    pairs.append(p)
+    f = bn(net.conv_input[1], f, True)
+    for b in net.blocks0:
+        f, p = block(b, c, f, sp_)
+        pairs.append(p)
+    for down, blocks in net.stages:
+        c, f, sp_, p = conv(down[0], c, f, sp_, False)
+        pairs.append(p)
+        f = bn(down[1], f, True)
+        for b in blocks:
+            f, p = block(b, c, f, sp_)
+            pairs.append(p)
+    c, f, sp_, p = conv(net.extra_conv[0], c, f, sp_, False)
+    pairs.append(p)
+    f = bn(net.extra_conv[1], f, True)
+    return oracle_mod.sparse_to_dense_bev(c, f, B, sp_), pairs
+
+
+def test_sparse_resnet3d_small(cuda, oracle_mod):
+    """Whole 21-conv backbone on a reduced grid (41 x 176 x 176 -> 2 x 22 x 22), lidar-like occupancy."""
+    from paddle3d_b200.layers import SparseResNet3D
+    cfg = dict(synth.C3, point_cloud_range=[-6.6, -6.6, -5.0, 6.6, 6.6, 3.0])
+    pts = synth.lidar_cloud(dict(cfg, point_cloud_range=[-20, -20, -5, 20, 20, 3]), 5, num_points=40000)
+    v, c, n, nv = oracle_mod.hard_voxelize(pts, cfg["voxel_size"], cfg["point_cloud_range"], 10, 20000)
+    k = int(nv[0])
+    assert k > 3000
+    feats = oracle_mod.voxel_mean(v, n, k)
+    coors = np.concatenate([np.zeros((k, 1), np.int32), c[:k]], 1)
+    net = SparseResNet3D(5, cfg["voxel_size"], cfg["point_cloud_range"]).init_weight(seed=3, device=cuda, randomize_bn=True)
+    assert net.sparse_shape == [41, 176, 176]
+    got = net(_t(cuda, feats), _t(cuda, coors), 1).cpu().numpy()
+    want, pairs = _oracle_resnet(oracle_mod, net, coors, feats, 1)
+    assert got.shape == want.shape == (1, 256, 22, 22)
+    scale = np.abs(want).max()
+    np.testing.assert_allclose(got, want, rtol=1e-4, atol=1e-4 * scale)
+    assert (want != 0).mean() > 0.05
