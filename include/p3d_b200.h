@@ -178,6 +178,12 @@ int p3d_sparse_affine_act(const float *x, const int32_t *n_dev, int64_t n_cap, i
  *   precision: P3D_CONV_FP32 = fp32 FMA on CUDA cores; P3D_CONV_TF32X3 = tcgen05 tensor cores with
  *   3xTF32 split accumulation in TMEM (fp32-level accuracy). */
 enum p3d_conv_precision { P3D_CONV_FP32 = 0, P3D_CONV_TF32X3 = 1 };
+/* Weight pre-pack for P3D_CONV_TF32X3 (once per layer): splits W [K, Cin, Cout] into tf32 hi / lo and lays it out
+ * as the shared-memory image the tensor-core kernel streams with cp.async.bulk.  Needs Cin, Cout multiples of
+ * 16 (Cin multiple of 32 above 32); returns P3D_ERR_UNSUPPORTED otherwise (use P3D_CONV_FP32 for such layers).
+ * With precision == P3D_CONV_TF32X3 the `weight` argument of p3d_sparse_conv_gather_gemm is this packed buffer. */
+size_t p3d_sparse_conv_packed_weight_bytes(int K, int Cin, int Cout);
+int p3d_sparse_conv_pack_weights(const float *weight, int K, int Cin, int Cout, float *packed, p3d_stream_t stream);
 int p3d_sparse_conv_gather_gemm(const float *in, const int32_t *nbr, const int32_t *n_out_dev, int64_t n_out_cap,
                                 int K, int Cin, int Cout, const float *weight, const float *scale,
                                 const float *shift, const float *residual, int relu, int precision, float *out,

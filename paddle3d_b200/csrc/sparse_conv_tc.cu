@@ -1,8 +1,374 @@
-// tcgen05 3xTF32 gather-GEMM (placeholder until the tensor-core kernel lands in this file).
+// Sparse-conv gather-GEMM on Blackwell tensor cores: tcgen05.mma kind::tf32, accumulators in TMEM,
+// 3xTF32 split (a = hi + lo, b = hi + lo; D += a_hi*b_hi + a_hi*b_lo + a_lo*b_hi) for fp32-level accuracy.
+//
+// One CTA owns 128 consecutive output rows (UMMA M = 128, N = Cout, fp32 accumulate in Cout TMEM columns)
+// and walks the K dimension = (active taps) x (Cin in chunks of KC <= 32 channels) through a ring of
+// shared-memory stages:
+//
+//   warps 0-3  producers: thread r gathers row nbr[row0 + r][tap] of the input (KC floats, 16-byte
+//              loads), splits every value into tf32 hi / lo and stores both into the stage's A tiles in the
+//              canonical no-swizzle K-major core-matrix layout (8 rows x 16 B per core matrix) — a missing
+//              neighbour is a zero row.  Thread 0 also fires ONE cp.async.bulk per stage that drops the
+//              pre-packed weight slice [hi | lo] for (tap, chunk) into the B tiles (TMA engine, mbarrier
+//              complete_tx).  Generic-proxy stores are made visible to the tensor core with
+//              fence.proxy.async before the mbarrier arrive.
+//   warp 4     one elected lane issues 3 x KC/8 tcgen05.mma per stage and tcgen05.commit's the stage back to
+//              the producers; after the last stage it commits the accumulator to the epilogue barrier.
+//   warps 0-3  epilogue: tcgen05.ld 32 lanes x 16 columns at a time, fused BN scale/shift (+bias), residual,
+//              ReLU, 64 B per thread row stores.
+//
+// Taps that no row of the tile uses are skipped for the whole tile (block-uniform bitmask).
+// Weights are packed once per layer by p3d_sparse_conv_pack_weights into exactly the shared-memory image:
+//   packed[tap][chunk g][hi|lo][KC/4 k-chunks][Cout rows][4 floats].
 #include "common.cuh"
 
-extern "C" int p3d_sparse_conv_gather_gemm_tf32x3(const float *, const int32_t *, const int32_t *, int64_t, int, int,
-                                                  int, const float *, const float *, const float *, const float *,
-                                                  int, float *, p3d_stream_t) {
+namespace p3d {
+namespace tc {
+
+constexpr int kM = 128;
+constexpr int kProducers = 128;
+constexpr int kThreads = 160;  // 4 producer/epilogue warps + 1 MMA warp
+
+__host__ __device__ constexpr int kc_of(int cin) { return cin < 32 ? cin : 32; }
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  const long long t0 = clock64();
+  uint32_t done;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (!done && clock64() - t0 > 4000000000ll) __trap();  // ~2 s: a protocol bug must not hang the GPU
+  } while (!done);
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+               "l"(src), "r"(bytes), "r"(bar)
+               : "memory");
+}
+
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+// K-major, no swizzle: core matrix = 8 rows x 16 B contiguous; LBO = distance between the two 16-byte
+// K-chunks of one MMA (K = 8 tf32), SBO = distance between 8-row groups (cute::UMMA::SmemDescriptor).
+__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((addr & 0x3ffffu) >> 4);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3fffu) << 16;
+  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3fffu) << 32;
+  d |= 1ull << 46;  // descriptor version 1 (Blackwell)
+  return d;         // base_offset 0, lbo_mode 0, layout_type 0 = SWIZZLE_NONE
+}
+
+__device__ __forceinline__ void split_tf32(float x, float &hi, float &lo) {
+  uint32_t h;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
+  hi = __uint_as_float(h);
+  const float r = x - hi;  // exact in fp32
+  uint32_t l;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(r));
+  lo = __uint_as_float(l);
+}
+
+template <int CIN, int COUT>
+struct Cfg {
+  static constexpr int KC = kc_of(CIN);          // channels per stage
+  static constexpr int G = CIN / KC;             // stages per tap
+  static constexpr int CH = KC / 4;              // 16-byte k-chunks per stage
+  static constexpr int A_TILE = KC * kM * 4;     // bytes, one of hi / lo
+  static constexpr int B_TILE = KC * COUT * 4;   // bytes, one of hi / lo
+  static constexpr int STAGE = 2 * A_TILE + 2 * B_TILE;
+  static constexpr int STAGES = (STAGE * 4 <= 160 * 1024) ? 4 : ((STAGE * 3 <= 200 * 1024) ? 3 : 2);
+  static constexpr int TMEM_COLS = COUT < 32 ? 32 : COUT;
+  static constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(COUT >> 3) << 17) |
+                                    (static_cast<uint32_t>(kM >> 4) << 24);
+  static_assert(CIN % 16 == 0 && COUT % 16 == 0 && COUT <= 256, "tensor-core path needs 16-channel multiples");
+};
+
+template <int CIN, int COUT>
+__global__ void __launch_bounds__(kThreads, 1) gather_gemm_tf32x3_kernel(const float *__restrict__ in,
+                                                                         const int32_t *__restrict__ nbr,
+                                                                         const int32_t *__restrict__ n_out_dev,
+                                                                         long long n_cap, int K,
+                                                                         const float *__restrict__ packed_w,
+                                                                         const float *__restrict__ scale,
+                                                                         const float *__restrict__ shift,
+                                                                         const float *__restrict__ residual, int relu,
+                                                                         float *__restrict__ out) {
+  using C = Cfg<CIN, COUT>;
+  const long long n = n_out_dev ? min(static_cast<long long>(n_out_dev[0]), n_cap) : n_cap;
+  const long long row0 = static_cast<long long>(blockIdx.x) * kM;
+  if (row0 >= n) return;
+  const int rows = static_cast<int>(min(static_cast<long long>(kM), n - row0));
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t *stage_base = smem;                                              // STAGES x STAGE
+  int32_t *s_nbr = reinterpret_cast<int32_t *>(smem + C::STAGES * C::STAGE);  // [kM][K]
+  __shared__ __align__(8) unsigned long long s_bar[2 * 4 + 1];              // full[4], empty[4], tmem_full
+  __shared__ uint32_t s_tmem_base;
+  __shared__ uint32_t s_active;                                             // bit t: some row uses tap t (K <= 32)
+
+  const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
+  if (tid == 0) s_active = 0u;
+  for (int q = tid; q < kM * K; q += kThreads) s_nbr[q] = (q < rows * K) ? nbr[row0 * K + q] : -1;
+  if (tid == kProducers) {  // first lane of the MMA warp
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(smem_u32(&s_bar[s]), kProducers + 1);  // 128 row arrivals + 1 arrive.expect_tx (weights)
+      mbar_init(smem_u32(&s_bar[4 + s]), 1);           // tcgen05.commit
+    }
+    mbar_init(smem_u32(&s_bar[8]), 1);
+    fence_mbar_init();
+  }
+  if (wid == 4) {  // TMEM allocation is warp-collective
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)),
+                 "r"(static_cast<uint32_t>(C::TMEM_COLS))
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  // which taps does this tile touch at all?
+  if (tid < kProducers) {
+    uint32_t mine = 0u;
+    for (int t = 0; t < K; ++t) mine |= (s_nbr[tid * K + t] >= 0) ? (1u << t) : 0u;
+    mine = __reduce_or_sync(0xffffffffu, mine);
+    if (lane == 0 && mine) atomicOr(&s_active, mine);
+  }
+  __syncthreads();
+  const uint32_t active = s_active;
+  const uint32_t tmem_base = s_tmem_base;
+  const int n_stage_uses = __popc(active) * C::G;
+
+  if (wid < 4) {
+    // ------------------------------------------------------------------ producers
+    const int r = tid;
+    const uint32_t a_off = static_cast<uint32_t>((r >> 3) * 128 + (r & 7) * 16);
+    int use = 0;
+    for (int t = 0; t < K; ++t) {
+      if (!((active >> t) & 1u)) continue;
+      const int src = s_nbr[r * K + t];
+      for (int g = 0; g < C::G; ++g, ++use) {
+        const int s = use % C::STAGES;
+        const uint32_t ph = static_cast<uint32_t>((use / C::STAGES) & 1);
+        mbar_wait(smem_u32(&s_bar[4 + s]), ph ^ 1u);  // slot free (first pass returns at once)
+        uint8_t *st = stage_base + s * C::STAGE;
+        if (tid == 0) {
+          const uint32_t bytes = 2u * C::B_TILE;
+          mbar_arrive_expect_tx(smem_u32(&s_bar[s]), bytes);
+          bulk_g2s(smem_u32(st + 2 * C::A_TILE), packed_w + (static_cast<size_t>(t) * C::G + g) * (2 * C::KC * COUT),
+                   bytes, smem_u32(&s_bar[s]));
+        }
+        float4 v[C::CH];
+        if (src >= 0) {
+          const float4 *p = reinterpret_cast<const float4 *>(in + static_cast<size_t>(src) * CIN + g * C::KC);
+#pragma unroll
+          for (int c = 0; c < C::CH; ++c) v[c] = __ldg(p + c);
+        } else {
+#pragma unroll
+          for (int c = 0; c < C::CH; ++c) v[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int c = 0; c < C::CH; ++c) {
+          float4 h, l;
+          split_tf32(v[c].x, h.x, l.x);
+          split_tf32(v[c].y, h.y, l.y);
+          split_tf32(v[c].z, h.z, l.z);
+          split_tf32(v[c].w, h.w, l.w);
+          *reinterpret_cast<float4 *>(st + c * (kM * 16) + a_off) = h;
+          *reinterpret_cast<float4 *>(st + C::A_TILE + c * (kM * 16) + a_off) = l;
+        }
+        fence_proxy_async();
+        mbar_arrive(smem_u32(&s_bar[s]));
+      }
+    }
+    // ------------------------------------------------------------------ epilogue
+    mbar_wait(smem_u32(&s_bar[8]), 0u);
+    tc_fence_after();
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(wid * 32) << 16);
+    const bool live = r < rows;
+    float *orow = out + (row0 + r) * COUT;
+    const float *rrow = residual ? residual + (row0 + r) * COUT : nullptr;
+#pragma unroll 1
+    for (int c0 = 0; c0 < COUT; c0 += 16) {
+      uint32_t a[16];
+      if (n_stage_uses > 0) {
+        asm volatile(
+            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, "
+            "%15}, [%16];"
+            : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]), "=r"(a[4]), "=r"(a[5]), "=r"(a[6]), "=r"(a[7]), "=r"(a[8]),
+              "=r"(a[9]), "=r"(a[10]), "=r"(a[11]), "=r"(a[12]), "=r"(a[13]), "=r"(a[14]), "=r"(a[15])
+            : "r"(taddr + static_cast<uint32_t>(c0)));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) a[j] = 0u;
+      }
+      if (live) {
+        float o[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          float v = __uint_as_float(a[j]);
+          if (scale) v = v * __ldg(scale + c0 + j);
+          if (shift) v = v + __ldg(shift + c0 + j);
+          if (rrow) v = v + rrow[c0 + j];
+          if (relu) v = fmaxf(v, 0.f);
+          o[j] = v;
+        }
+#pragma unroll
+        for (int j = 0; j < 16; j += 4)
+          *reinterpret_cast<float4 *>(orow + c0 + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+      }
+    }
+    tc_fence_before();
+  } else {
+    // ------------------------------------------------------------------ MMA issuer (warp 4)
+    if (n_stage_uses == 0) {
+      if (lane == 0) mbar_arrive(smem_u32(&s_bar[8]));
+    } else {
+      for (int use = 0; use < n_stage_uses; ++use) {
+        const int s = use % C::STAGES;
+        const uint32_t ph = static_cast<uint32_t>((use / C::STAGES) & 1);
+        mbar_wait(smem_u32(&s_bar[s]), ph);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t st = smem_u32(stage_base + s * C::STAGE);
+          const uint32_t a_hi = st, a_lo = st + C::A_TILE, b_hi = st + 2 * C::A_TILE, b_lo = b_hi + C::B_TILE;
+#pragma unroll
+          for (int j = 0; j < C::KC / 8; ++j) {
+            const uint32_t ao = static_cast<uint32_t>(2 * j) * (kM * 16), bo = static_cast<uint32_t>(2 * j) * (COUT * 16);
+            const uint64_t dah = smem_desc(a_hi + ao, kM * 16, 128), dal = smem_desc(a_lo + ao, kM * 16, 128);
+            const uint64_t dbh = smem_desc(b_hi + bo, COUT * 16, 128), dbl = smem_desc(b_lo + bo, COUT * 16, 128);
+            umma_tf32(tmem_base, dal, dbh, C::IDESC, (use | j) ? 1u : 0u);  // small terms first
+            umma_tf32(tmem_base, dah, dbl, C::IDESC, 1u);
+            umma_tf32(tmem_base, dah, dbh, C::IDESC, 1u);
+          }
+          umma_commit(smem_u32(&s_bar[4 + s]));                               // stage back to the producers
+          if (use == n_stage_uses - 1) umma_commit(smem_u32(&s_bar[8]));      // accumulator ready
+        }
+        __syncwarp();
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (wid == 4) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"(static_cast<uint32_t>(C::TMEM_COLS))
+                 : "memory");
+  }
+}
+
+// packed[tap][g][hl][c][n][j] = split(W[tap][g*KC + 4c + j][n])
+__global__ void __launch_bounds__(256) pack_weights_kernel(const float *__restrict__ w, int K, int Cin, int Cout,
+                                                           float *__restrict__ packed) {
+  const long long q = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const long long total = static_cast<long long>(K) * Cin * Cout;
+  if (q >= total) return;
+  const int KC = kc_of(Cin), G = Cin / KC, CH = KC / 4;
+  const int n = static_cast<int>(q % Cout);
+  const int ci = static_cast<int>((q / Cout) % Cin);
+  const int t = static_cast<int>(q / (static_cast<long long>(Cout) * Cin));
+  const int g = ci / KC, c = (ci % KC) / 4, j = ci & 3;
+  float hi, lo;
+  split_tf32(w[q], hi, lo);
+  const size_t tile = static_cast<size_t>(KC) * Cout;  // floats in one hi (or lo) slice
+  const size_t base = (static_cast<size_t>(t) * G + g) * 2 * tile;
+  const size_t off = (static_cast<size_t>(c) * Cout + n) * 4 + j;
+  (void)CH;
+  packed[base + off] = hi;
+  packed[base + tile + off] = lo;
+}
+
+template <int CIN, int COUT>
+int launch(const float *in, const int32_t *nbr, const int32_t *n_out_dev, int64_t n_cap, int K, const float *packed,
+           const float *scale, const float *shift, const float *residual, int relu, float *out, cudaStream_t st) {
+  using C = Cfg<CIN, COUT>;
+  const size_t smem = static_cast<size_t>(C::STAGES) * C::STAGE + static_cast<size_t>(kM) * K * sizeof(int32_t) + 1024;
+  if (smem > 227 * 1024) return P3D_ERR_UNSUPPORTED;
+  auto kern = gather_gemm_tf32x3_kernel<CIN, COUT>;
+  P3D_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  kern<<<div_up(n_cap, kM), kThreads, smem, st>>>(in, nbr, n_out_dev, n_cap, K, packed, scale, shift, residual, relu,
+                                                  out);
+  P3D_LAUNCH_CHECK();
+  return P3D_OK;
+}
+
+}  // namespace tc
+}  // namespace p3d
+
+using namespace p3d;
+
+extern "C" size_t p3d_sparse_conv_packed_weight_bytes(int K, int Cin, int Cout) {
+  if (K < 1 || Cin < 16 || Cout < 16 || Cin % 16 || Cout % 16) return 0;
+  return align_up(static_cast<size_t>(K) * Cin * Cout * 2 * sizeof(float));
+}
+
+extern "C" int p3d_sparse_conv_pack_weights(const float *weight, int K, int Cin, int Cout, float *packed,
+                                            p3d_stream_t stream) {
+  if (!weight || !packed || K < 1) return P3D_ERR_INVALID_ARG;
+  if (Cin < 16 || Cout < 16 || Cin % 16 || Cout % 16 || (Cin > 32 && Cin % 32)) return P3D_ERR_UNSUPPORTED;
+  const long long total = static_cast<long long>(K) * Cin * Cout;
+  tc::pack_weights_kernel<<<div_up(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(weight, K, Cin, Cout,
+                                                                                            packed);
+  P3D_LAUNCH_CHECK();
+  return P3D_OK;
+}
+
+extern "C" int p3d_sparse_conv_gather_gemm_tf32x3(const float *in, const int32_t *nbr, const int32_t *n_out_dev,
+                                                  int64_t n_out_cap, int K, int Cin, int Cout, const float *weight,
+                                                  const float *scale, const float *shift, const float *residual,
+                                                  int relu, float *out, p3d_stream_t stream) {
+  if (n_out_cap < 0 || K < 1 || K > 32 || !weight || (n_out_cap && (!in || !nbr || !out))) return P3D_ERR_INVALID_ARG;
+  if (n_out_cap == 0) return P3D_OK;
+  if ((reinterpret_cast<uintptr_t>(in) & 15) || (reinterpret_cast<uintptr_t>(out) & 15) ||
+      (reinterpret_cast<uintptr_t>(weight) & 15))
+    return P3D_ERR_INVALID_ARG;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define P3D_TC_CASE(CI, CO)                                                                                    \
+  if (Cin == CI && Cout == CO)                                                                                 \
+    return tc::launch<CI, CO>(in, nbr, n_out_dev, n_out_cap, K, weight, scale, shift, residual, relu, out, st);
+  P3D_TC_CASE(16, 16)
+  P3D_TC_CASE(16, 32)
+  P3D_TC_CASE(32, 32)
+  P3D_TC_CASE(32, 64)
+  P3D_TC_CASE(64, 64)
+  P3D_TC_CASE(64, 128)
+  P3D_TC_CASE(128, 128)
+#undef P3D_TC_CASE
   return P3D_ERR_UNSUPPORTED;
 }

@@ -188,6 +188,18 @@ class _ConvBase(_Layer):
             self.bias = torch.from_numpy(b).to(device)
         return self
 
+    def _packed_weight(self, K):
+        """tf32 hi/lo shared-memory image of the weights, built once per layer (p3d_sparse_conv_pack_weights)."""
+        pk = getattr(self, "_packed", None)
+        if pk is None or pk[0] != self.weight.data_ptr():
+            L = lib()
+            nbytes = L.p3d_sparse_conv_packed_weight_bytes(K, self.in_channels, self.out_channels)
+            buf = torch.empty((nbytes // 4,), dtype=torch.float32, device=self.weight.device)
+            check(L.p3d_sparse_conv_pack_weights(ptr(self.weight), K, self.in_channels, self.out_channels, ptr(buf),
+                                                 stream(self.weight.device)), "sparse_conv_pack_weights")
+            self._packed = pk = (self.weight.data_ptr(), buf)
+        return pk[1]
+
     def set_parameters(self, weight, bias=None):
         self.weight = require_cuda(weight, "weight", torch.float32)
         self.bias = require_cuda(bias, "bias", torch.float32) if bias is not None else None
@@ -201,8 +213,11 @@ class _ConvBase(_Layer):
         p.x, p.K, p.cin, p.cout = x, K, self.in_channels, self.out_channels
         p.weight, p.scale, p.shift, p.residual, p.relu = self.weight, None, self.bias, None, False
         p.precision = self.precision if self.precision is not None else _default_precision[0]
-        if p.precision == TF32X3 and (self.in_channels % 16 or self.out_channels % 16):
-            p.precision = FP32  # the 5-channel input layer stays on the exact fp32 path
+        if p.precision == TF32X3:
+            if not lib().p3d_sparse_conv_packed_weight_bytes(K, self.in_channels, self.out_channels) or K > 32:
+                p.precision = FP32  # e.g. the 5-channel input layer stays on the exact fp32 path
+            else:
+                p.weight = self._packed_weight(K)
         if self.subm:
             index = x.index
             p.nbr = index.subm_rulebook(self.kernel_size, self.key)

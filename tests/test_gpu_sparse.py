@@ -28,7 +28,7 @@ def _rand_sites(rng, B, D, H, W, p):
     return c
 
 
-@pytest.mark.parametrize("precision", [0])
+@pytest.mark.parametrize("precision", [0, 1])
 @pytest.mark.parametrize("subm,ks,st,pd,cin,cout", [
     (True, 3, 1, 1, 5, 16), (True, 3, 1, 1, 16, 16), (True, 3, 1, 1, 64, 64), (True, 3, 1, 1, 128, 128),
     (False, 3, 2, 1, 16, 32), (False, 3, 2, [0, 1, 1], 64, 128), (False, (3, 1, 1), (2, 1, 1), 0, 128, 128),
@@ -120,7 +120,8 @@ def _oracle_resnet(oracle_mod, net, coords, feats, B):
     return oracle_mod.sparse_to_dense_bev(c, f, B, sp_), pairs
 
 
-def test_sparse_resnet3d_small(cuda, oracle_mod):
+@pytest.mark.parametrize("precision", [0, 1])
+def test_sparse_resnet3d_small(cuda, oracle_mod, precision):
     """Whole 21-conv backbone on a reduced grid (41 x 176 x 176 -> 2 x 22 x 22), lidar-like occupancy."""
     from paddle3d_b200.layers import SparseResNet3D
     cfg = dict(synth.C3, point_cloud_range=[-6.6, -6.6, -5.0, 6.6, 6.6, 3.0])
@@ -131,6 +132,7 @@ def test_sparse_resnet3d_small(cuda, oracle_mod):
     feats = oracle_mod.voxel_mean(v, n, k)
     coors = np.concatenate([np.zeros((k, 1), np.int32), c[:k]], 1)
     net = SparseResNet3D(5, cfg["voxel_size"], cfg["point_cloud_range"]).init_weight(seed=3, device=cuda, randomize_bn=True)
+    net.set_precision(precision)
     assert net.sparse_shape == [41, 176, 176]
     got = net(_t(cuda, feats), _t(cuda, coors), 1).cpu().numpy()
     want, pairs = _oracle_resnet(oracle_mod, net, coors, feats, 1)
