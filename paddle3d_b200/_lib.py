@@ -69,7 +69,16 @@ def lib():
     return _lib
 
 
+_DEBUG_SYNC = bool(os.environ.get("P3D_DEBUG_SYNC"))
+
+
 def check(rc, what):
+    if _DEBUG_SYNC and rc == 0:  # debugging aid: surface asynchronous kernel faults at the call that caused them
+        import torch
+        try:
+            torch.cuda.synchronize()
+        except Exception as e:  # noqa: BLE001
+            raise P3DError("%s: kernel fault (%s)" % (what, e))
     if rc != 0:
         l = lib()
         msg = l.p3d_status_string(rc).decode()

@@ -36,21 +36,24 @@ __global__ void __launch_bounds__(64) nms_mask_kernel(int n, float thr, const fl
   const int rb = blockIdx.y, cb = blockIdx.x;
   if (cb < rb) return;
   const int rows = min(n - rb * 64, 64), cols = min(n - cb * 64, 64);
-  __shared__ float sb[64 * 7];
-  for (int k = threadIdx.x; k < cols * 7; k += 64) sb[k] = boxes[static_cast<size_t>(cb) * 64 * 7 + k];
+  __shared__ float s_col[64 * 7], s_row[64 * 7];
+  __shared__ unsigned short s_pairs[64 * 64];
+  __shared__ unsigned long long s_bits[64];
+  __shared__ int s_cnt[3];
+  for (int k = threadIdx.x; k < cols * 7; k += 64) s_col[k] = boxes[static_cast<size_t>(cb) * 64 * 7 + k];
+  for (int k = threadIdx.x; k < rows * 7; k += 64) s_row[k] = boxes[static_cast<size_t>(rb) * 64 * 7 + k];
   __syncthreads();
-  if (threadIdx.x >= rows) return;
-  const int i = rb * 64 + threadIdx.x;
-  float cur[7];
-#pragma unroll
-  for (int k = 0; k < 7; ++k) cur[k] = boxes[static_cast<size_t>(i) * 7 + k];
   unsigned long long t = 0ull;
-  const int start = (rb == cb) ? threadIdx.x + 1 : 0;
-  for (int j = start; j < cols; ++j) {
-    const float v = kNormal ? geom::iou_axis_aligned(cur, sb + j * 7) : geom::iou_rotated(cur, sb + j * 7);
-    if (v > thr) t |= 1ull << j;
+  if (kNormal) {
+    if (threadIdx.x < rows) {
+      const int start = (rb == cb) ? threadIdx.x + 1 : 0;
+      for (int j = start; j < cols; ++j)
+        if (geom::iou_axis_aligned(s_row + threadIdx.x * 7, s_col + j * 7) > thr) t |= 1ull << j;
+    }
+  } else {
+    t = nms_rotated_tile(s_row, s_col, rows, cols, rb == cb, thr, s_pairs, s_bits, s_cnt);
   }
-  mask[static_cast<size_t>(i) * ((n + 63) / 64) + cb] = t;
+  if (threadIdx.x < rows) mask[static_cast<size_t>(rb * 64 + threadIdx.x) * ((n + 63) / 64) + cb] = t;
 }
 
 __global__ void __launch_bounds__(256) nms_reduce_kernel(const unsigned long long *__restrict__ mask, int n,

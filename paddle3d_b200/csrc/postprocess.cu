@@ -168,18 +168,17 @@ __global__ void __launch_bounds__(64) cpp_nms_mask_kernel(CppAttrs at, CppWs w) 
   const int rows = min(n - rb * 64, 64), cols = min(n - cb * 64, 64);
   const float *boxes = w.boxes + static_cast<size_t>(t) * at.HW * at.dims;
   const int32_t *order = w.order + static_cast<size_t>(t) * at.pre_max;
-  __shared__ float sb[64 * 7];
-  if (threadIdx.x < cols) fetch_nms_box(boxes + static_cast<size_t>(order[cb * 64 + threadIdx.x]) * at.dims, at.dims, sb + threadIdx.x * 7);
+  __shared__ float s_col[64 * 7], s_row[64 * 7];
+  __shared__ unsigned short s_pairs[64 * 64];
+  __shared__ unsigned long long s_bits[64];
+  __shared__ int s_cnt[3];
+  if (threadIdx.x < cols)
+    fetch_nms_box(boxes + static_cast<size_t>(order[cb * 64 + threadIdx.x]) * at.dims, at.dims, s_col + threadIdx.x * 7);
+  if (threadIdx.x < rows)
+    fetch_nms_box(boxes + static_cast<size_t>(order[rb * 64 + threadIdx.x]) * at.dims, at.dims, s_row + threadIdx.x * 7);
   __syncthreads();
-  if (threadIdx.x >= rows) return;
-  const int i = rb * 64 + threadIdx.x;
-  float cur[7];
-  fetch_nms_box(boxes + static_cast<size_t>(order[i]) * at.dims, at.dims, cur);
-  unsigned long long bits = 0ull;
-  const int start = (rb == cb) ? threadIdx.x + 1 : 0;
-  for (int j = start; j < cols; ++j)
-    if (geom::iou_rotated(cur, sb + j * 7) > at.iou_thr) bits |= 1ull << j;
-  w.mask[(static_cast<size_t>(t) * at.pre_max + i) * at.cbmax + cb] = bits;
+  const unsigned long long bits = nms_rotated_tile(s_row, s_col, rows, cols, rb == cb, at.iou_thr, s_pairs, s_bits, s_cnt);
+  if (threadIdx.x < rows) w.mask[(static_cast<size_t>(t) * at.pre_max + rb * 64 + threadIdx.x) * at.cbmax + cb] = bits;
 }
 
 __global__ void __launch_bounds__(256) cpp_greedy_kernel(CppAttrs at, CppWs w) {

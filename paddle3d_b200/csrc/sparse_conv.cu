@@ -101,20 +101,22 @@ __global__ void __launch_bounds__(256) rb_neighbors_kernel(const int32_t *__rest
                                                            const unsigned long long *__restrict__ tab, uint32_t mask,
                                                            uint32_t shift, int subm, int32_t *__restrict__ nbr) {
   const int K = d.kd * d.kh * d.kw;
-  const long long q = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long n = n_dev ? min(static_cast<long long>(n_dev[0]), n_cap) : n_cap;
-  if (q >= n * K) return;
-  const int o = static_cast<int>(q / K), k = static_cast<int>(q - static_cast<long long>(o) * K);
-  const int4 c = *reinterpret_cast<const int4 *>(out_coords + static_cast<size_t>(o) * 4);
-  const int kz = k / (d.kh * d.kw), ky = (k / d.kw) % d.kh, kx = k % d.kw;
-  const int iz = c.y * d.sd - d.pd + kz, iy = c.z * d.sh - d.ph + ky, ix = c.w * d.sw - d.pw + kx;
-  int r = -1;
-  if (subm && kz == d.kd / 2 && ky == d.kh / 2 && kx == d.kw / 2) {
-    r = o;
-  } else if (iz >= 0 && iz < d.D && iy >= 0 && iy < d.H && ix >= 0 && ix < d.W) {
-    r = lookup(tab, mask, shift, lin(c.x, iz, iy, ix, d.D, d.H, d.W));
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  // persistent grid-stride loop: the grid is sized for the SMs, not for the (much larger) capacity
+  for (long long q = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; q < n * K; q += stride) {
+    const int o = static_cast<int>(q / K), k = static_cast<int>(q - static_cast<long long>(o) * K);
+    const int4 c = *reinterpret_cast<const int4 *>(out_coords + static_cast<size_t>(o) * 4);
+    const int kz = k / (d.kh * d.kw), ky = (k / d.kw) % d.kh, kx = k % d.kw;
+    const int iz = c.y * d.sd - d.pd + kz, iy = c.z * d.sh - d.ph + ky, ix = c.w * d.sw - d.pw + kx;
+    int r = -1;
+    if (subm && kz == d.kd / 2 && ky == d.kh / 2 && kx == d.kw / 2) {
+      r = o;
+    } else if (iz >= 0 && iz < d.D && iy >= 0 && iy < d.H && ix >= 0 && ix < d.W) {
+      r = lookup(tab, mask, shift, lin(c.x, iz, iy, ix, d.D, d.H, d.W));
+    }
+    nbr[q] = r;
   }
-  nbr[q] = r;
 }
 
 // Strided conv: enumerate output sites.  Thread (i, k): candidate o = (in + pad - k) / stride.
@@ -124,41 +126,42 @@ __global__ void __launch_bounds__(256) rb_outputs_kernel(const int32_t *__restri
                                                          uint32_t shift, int32_t *__restrict__ out_coords,
                                                          int32_t *__restrict__ n_out_dev, int out_cap) {
   const int K = d.kd * d.kh * d.kw;
-  const long long q = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long n = n_dev ? min(static_cast<long long>(n_dev[0]), n_cap) : n_cap;
-  if (q >= n * K) return;
-  const int i = static_cast<int>(q / K), k = static_cast<int>(q - static_cast<long long>(i) * K);
-  const int4 c = *reinterpret_cast<const int4 *>(coords + static_cast<size_t>(i) * 4);
-  const int kz = k / (d.kh * d.kw), ky = (k / d.kw) % d.kh, kx = k % d.kw;
-  int oz = c.y + d.pd - kz, oy = c.z + d.ph - ky, ox = c.w + d.pw - kx;
-  if (oz < 0 || oy < 0 || ox < 0 || oz % d.sd || oy % d.sh || ox % d.sw) return;
-  oz /= d.sd;
-  oy /= d.sh;
-  ox /= d.sw;
-  if (oz >= d.oD || oy >= d.oH || ox >= d.oW) return;
-  const uint32_t key = lin(c.x, oz, oy, ox, d.oD, d.oH, d.oW);
-  uint32_t h = hash32(key) >> shift;
-  for (uint32_t probes = 0;; ++probes) {
-    if (probes > mask) {  // table full (far more sites than out_cap): cannot dedupe any more, flag overflow
-      n_out_dev[3] = 1;
-      return;
-    }
-    unsigned long long cur = tab_out[h];
-    if (cur == kEmpty) {
-      // claim the slot with a provisional row id; the winner numbers the site
-      const unsigned long long want = (static_cast<unsigned long long>(key) << 32) | 0xfffffffeu;
-      cur = atomicCAS(&tab_out[h], kEmpty, want);
-      if (cur == kEmpty) {
-        const int id = atomicAdd(&n_out_dev[2], 1);  // raw counter; clamped copy is published by rb_finish
-        if (id < out_cap) {
-          int4 oc = make_int4(c.x, oz, oy, ox);
-          *reinterpret_cast<int4 *>(out_coords + static_cast<size_t>(id) * 4) = oc;
-        }
-        return;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long q = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; q < n * K; q += stride) {
+    const int i = static_cast<int>(q / K), k = static_cast<int>(q - static_cast<long long>(i) * K);
+    const int4 c = *reinterpret_cast<const int4 *>(coords + static_cast<size_t>(i) * 4);
+    const int kz = k / (d.kh * d.kw), ky = (k / d.kw) % d.kh, kx = k % d.kw;
+    int oz = c.y + d.pd - kz, oy = c.z + d.ph - ky, ox = c.w + d.pw - kx;
+    if (oz < 0 || oy < 0 || ox < 0 || oz % d.sd || oy % d.sh || ox % d.sw) continue;
+    oz /= d.sd;
+    oy /= d.sh;
+    ox /= d.sw;
+    if (oz >= d.oD || oy >= d.oH || ox >= d.oW) continue;
+    const uint32_t key = lin(c.x, oz, oy, ox, d.oD, d.oH, d.oW);
+    uint32_t h = hash32(key) >> shift;
+    for (uint32_t probes = 0;; ++probes) {
+      if (probes > mask) {  // table full (far more sites than out_cap): cannot dedupe any more, flag overflow
+        n_out_dev[3] = 1;
+        break;
       }
+      unsigned long long cur = tab_out[h];
+      if (cur == kEmpty) {
+        // claim the slot; the winner numbers the site
+        const unsigned long long want = (static_cast<unsigned long long>(key) << 32) | 0xfffffffeu;
+        cur = atomicCAS(&tab_out[h], kEmpty, want);
+        if (cur == kEmpty) {
+          const int id = atomicAdd(&n_out_dev[2], 1);  // raw counter; the clamped copy is published by rb_finish
+          if (id < out_cap) {
+            int4 oc = make_int4(c.x, oz, oy, ox);
+            *reinterpret_cast<int4 *>(out_coords + static_cast<size_t>(id) * 4) = oc;
+          }
+          break;
+        }
+      }
+      if (static_cast<uint32_t>(cur >> 32) == key) break;
+      h = (h + 1) & mask;
     }
-    if (static_cast<uint32_t>(cur >> 32) == key) return;
-    h = (h + 1) & mask;
   }
 }
 
@@ -279,6 +282,55 @@ __global__ void __launch_bounds__(256) rows_affine_act_kernel(const float *__res
   out[q] = v;
 }
 
+// Few input channels (the 5 -> 16 input layer, sparse_resnet.py:125-127): one thread per output row keeps all
+// COUT accumulators in registers, weights of all taps live in shared memory; exact fp32 FMA chain.
+template <int COUT>
+__global__ void __launch_bounds__(128) small_cin_kernel(const float *__restrict__ in, const int32_t *__restrict__ nbr,
+                                                        const int32_t *__restrict__ n_out_dev, long long n_cap, int K,
+                                                        int Cin, const float *__restrict__ weight,
+                                                        const float *__restrict__ scale, const float *__restrict__ shift,
+                                                        const float *__restrict__ residual, int relu,
+                                                        float *__restrict__ out) {
+  extern __shared__ float s_w[];  // [K][Cin][COUT]
+  const long long n = n_out_dev ? min(static_cast<long long>(n_out_dev[0]), n_cap) : n_cap;
+  if (static_cast<long long>(blockIdx.x) * blockDim.x >= n) return;
+  for (int q = threadIdx.x; q < K * Cin * COUT; q += blockDim.x) s_w[q] = weight[q];
+  __syncthreads();
+  const long long row = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (row >= n) return;
+  float acc[COUT];
+#pragma unroll
+  for (int c = 0; c < COUT; ++c) acc[c] = 0.f;
+  const int32_t *nb = nbr + row * K;
+  for (int k = 0; k < K; ++k) {
+    const int src = __ldg(nb + k);
+    if (src < 0) continue;
+    const float *x = in + static_cast<size_t>(src) * Cin;
+    const float *w = s_w + k * Cin * COUT;
+    for (int ci = 0; ci < Cin; ++ci) {
+      const float xv = __ldg(x + ci);
+#pragma unroll
+      for (int c = 0; c < COUT; ++c) acc[c] = fmaf(xv, w[ci * COUT + c], acc[c]);
+    }
+  }
+  float *o = out + row * COUT;
+#pragma unroll
+  for (int c = 0; c < COUT; ++c) {
+    float v = acc[c];
+    if (scale) v = v * scale[c];
+    if (shift) v = v + shift[c];
+    if (residual) v = v + residual[row * COUT + c];
+    if (relu) v = fmaxf(v, 0.f);
+    o[c] = v;
+  }
+}
+
+unsigned int persistent_grid(long long work_items) {
+  const long long need = (work_items + 255) / 256;
+  const long long cap = static_cast<long long>(kNumSMs) * 8;  // 8 CTAs of 256 threads per SM = full occupancy
+  return static_cast<unsigned int>(need < cap ? (need > 0 ? need : 1) : cap);
+}
+
 int make_dims(int batch, const int *sp, const int *ks, const int *st, const int *pd, int subm, Dims *d) {
   if (!sp || !ks || batch < 1) return P3D_ERR_INVALID_ARG;
   d->B = batch;
@@ -345,7 +397,7 @@ extern "C" int p3d_sparse_rulebook_subm(const int32_t *coords, const int32_t *n_
   rb_insert_kernel<<<div_up(n_in_cap, 256), 256, 0, st>>>(coords, n_in_dev, static_cast<int>(n_in_cap), d, w.tab_in,
                                                          w.cap_in - 1, w.shift_in);
   P3D_LAUNCH_CHECK();
-  rb_neighbors_kernel<<<div_up(n_in_cap * K, 256), 256, 0, st>>>(coords, n_in_dev, n_in_cap, d, w.tab_in,
+  rb_neighbors_kernel<<<persistent_grid(n_in_cap * K), 256, 0, st>>>(coords, n_in_dev, n_in_cap, d, w.tab_in,
                                                                  w.cap_in - 1, w.shift_in, 1, nbr);
   P3D_LAUNCH_CHECK();
   return P3D_OK;
@@ -376,14 +428,14 @@ extern "C" int p3d_sparse_rulebook_conv(const int32_t *coords, const int32_t *n_
     rb_insert_kernel<<<div_up(n_in_cap, 256), 256, 0, st>>>(coords, n_in_dev, static_cast<int>(n_in_cap), d,
                                                            w.tab_in, w.cap_in - 1, w.shift_in);
     P3D_LAUNCH_CHECK();
-    rb_outputs_kernel<<<div_up(n_in_cap * K, 256), 256, 0, st>>>(coords, n_in_dev, n_in_cap, d, w.tab_out,
+    rb_outputs_kernel<<<persistent_grid(n_in_cap * K), 256, 0, st>>>(coords, n_in_dev, n_in_cap, d, w.tab_out,
                                                                  w.cap_out - 1, w.shift_out, out_coords, n_out_dev,
                                                                  static_cast<int>(out_cap));
     P3D_LAUNCH_CHECK();
   }
   rb_finish_kernel<<<1, 1, 0, st>>>(n_out_dev, static_cast<int>(out_cap));
   P3D_LAUNCH_CHECK();
-  rb_neighbors_kernel<<<div_up(out_cap * K, 256), 256, 0, st>>>(out_coords, n_out_dev, out_cap, d, w.tab_in,
+  rb_neighbors_kernel<<<persistent_grid(out_cap * K), 256, 0, st>>>(out_coords, n_out_dev, out_cap, d, w.tab_in,
                                                                w.cap_in - 1, w.shift_in, 0, nbr);
   P3D_LAUNCH_CHECK();
   return P3D_OK;
@@ -397,6 +449,17 @@ extern "C" int p3d_sparse_conv_gather_gemm_fp32(const float *in, const int32_t *
     return P3D_ERR_INVALID_ARG;
   if (n_out_cap == 0) return P3D_OK;
   if ((Cin % 4 == 0) && (reinterpret_cast<uintptr_t>(in) & 15)) return P3D_ERR_INVALID_ARG;
+  if (Cin <= 8 && (Cout == 16 || Cout == 32) && static_cast<size_t>(K) * Cin * Cout * 4 <= 40 * 1024) {
+    const size_t sw = static_cast<size_t>(K) * Cin * Cout * sizeof(float);
+    if (Cout == 16)
+      small_cin_kernel<16><<<div_up(n_out_cap, 128), 128, sw, static_cast<cudaStream_t>(stream)>>>(
+          in, nbr, n_out_dev, n_out_cap, K, Cin, weight, scale, shift, residual, relu, out);
+    else
+      small_cin_kernel<32><<<div_up(n_out_cap, 128), 128, sw, static_cast<cudaStream_t>(stream)>>>(
+          in, nbr, n_out_dev, n_out_cap, K, Cin, weight, scale, shift, residual, relu, out);
+    P3D_LAUNCH_CHECK();
+    return P3D_OK;
+  }
   const size_t smem = static_cast<size_t>(TM) * K * sizeof(int);
   if (smem > 40 * 1024) return P3D_ERR_UNSUPPORTED;
   dim3 grid(div_up(n_out_cap, TM), div_up(Cout, TN));

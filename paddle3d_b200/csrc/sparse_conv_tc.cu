@@ -27,9 +27,9 @@ namespace tc {
 
 constexpr int kM = 128;
 constexpr int kProducers = 128;
-constexpr int kThreads = 160;  // 4 producer/epilogue warps + 1 MMA warp
+constexpr int kThreads = 192;  // 4 producer/epilogue warps + 1 MMA warp + 1 weight-TMA warp
 
-__host__ __device__ constexpr int kc_of(int cin) { return cin < 32 ? cin : 32; }
+__host__ __device__ constexpr int kc_of(int cin) { return cin < 16 ? cin : 16; }  // channels per pipeline stage
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
 
@@ -108,8 +108,14 @@ struct Cfg {
   static constexpr int CH = KC / 4;              // 16-byte k-chunks per stage
   static constexpr int A_TILE = KC * kM * 4;     // bytes, one of hi / lo
   static constexpr int B_TILE = KC * COUT * 4;   // bytes, one of hi / lo
-  static constexpr int STAGE = 2 * A_TILE + 2 * B_TILE;
-  static constexpr int STAGES = (STAGE * 4 <= 160 * 1024) ? 4 : ((STAGE * 3 <= 200 * 1024) ? 3 : 2);
+  static constexpr int A_STAGE = 2 * A_TILE;      // hi + lo
+  static constexpr int B_STAGE = 2 * B_TILE;      // hi + lo (one cp.async.bulk)
+  // two independent rings (<= 96 KB together: two CTAs per SM): SA slots of gathered rows, SB slots of weights.
+  // The weight ring is deeper so that the TMA latency never sits on the gather -> MMA critical path.
+  static constexpr int SA = (COUT <= 64) ? 4 : 3;
+  static constexpr int SB_RAW = (96 * 1024 - SA * A_STAGE) / B_STAGE;
+  static constexpr int SB = SB_RAW > 8 ? 8 : SB_RAW;
+  static constexpr int RING_BYTES = SA * A_STAGE + SB * B_STAGE;
   static constexpr int TMEM_COLS = COUT < 32 ? 32 : COUT;
   static constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(COUT >> 3) << 17) |
                                     (static_cast<uint32_t>(kM >> 4) << 24);
@@ -117,7 +123,7 @@ struct Cfg {
 };
 
 template <int CIN, int COUT>
-__global__ void __launch_bounds__(kThreads, 1) gather_gemm_tf32x3_kernel(const float *__restrict__ in,
+__global__ void __launch_bounds__(kThreads, 2) gather_gemm_tf32x3_kernel(const float *__restrict__ in,
                                                                          const int32_t *__restrict__ nbr,
                                                                          const int32_t *__restrict__ n_out_dev,
                                                                          long long n_cap, int K,
@@ -134,9 +140,12 @@ __global__ void __launch_bounds__(kThreads, 1) gather_gemm_tf32x3_kernel(const f
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t *stage_base = smem;                                              // STAGES x STAGE
-  int32_t *s_nbr = reinterpret_cast<int32_t *>(smem + C::STAGES * C::STAGE);  // [kM][K]
-  __shared__ __align__(8) unsigned long long s_bar[2 * 4 + 1];              // full[4], empty[4], tmem_full
+  uint8_t *a_base = smem;                                                  // SA x A_STAGE
+  uint8_t *b_base = smem + C::SA * C::A_STAGE;                             // SB x B_STAGE
+  int32_t *s_nbr = reinterpret_cast<int32_t *>(smem + C::RING_BYTES);      // [kM][K]
+  // barriers: a_full[4] a_empty[4] b_full[8] b_empty[8] tmem_full
+  __shared__ __align__(8) unsigned long long s_bar[4 + 4 + 8 + 8 + 1];
+  constexpr int kAF = 0, kAE = 4, kBF = 8, kBE = 16, kTF = 24;
   __shared__ uint32_t s_tmem_base;
   __shared__ uint32_t s_active;                                             // bit t: some row uses tap t (K <= 32)
 
@@ -144,11 +153,15 @@ __global__ void __launch_bounds__(kThreads, 1) gather_gemm_tf32x3_kernel(const f
   if (tid == 0) s_active = 0u;
   for (int q = tid; q < kM * K; q += kThreads) s_nbr[q] = (q < rows * K) ? nbr[row0 * K + q] : -1;
   if (tid == kProducers) {  // first lane of the MMA warp
-    for (int s = 0; s < C::STAGES; ++s) {
-      mbar_init(smem_u32(&s_bar[s]), kProducers + 1);  // 128 row arrivals + 1 arrive.expect_tx (weights)
-      mbar_init(smem_u32(&s_bar[4 + s]), 1);           // tcgen05.commit
+    for (int s = 0; s < C::SA; ++s) {
+      mbar_init(smem_u32(&s_bar[kAF + s]), 32);        // the 32 lanes of the slot's producer warp
+      mbar_init(smem_u32(&s_bar[kAE + s]), 1);         // tcgen05.commit
     }
-    mbar_init(smem_u32(&s_bar[8]), 1);
+    for (int s = 0; s < C::SB; ++s) {
+      mbar_init(smem_u32(&s_bar[kBF + s]), 1);         // arrive.expect_tx + bulk-copy bytes
+      mbar_init(smem_u32(&s_bar[kBE + s]), 1);         // tcgen05.commit
+    }
+    mbar_init(smem_u32(&s_bar[kTF]), 1);
     fence_mbar_init();
   }
   if (wid == 4) {  // TMEM allocation is warp-collective
@@ -175,48 +188,58 @@ __global__ void __launch_bounds__(kThreads, 1) gather_gemm_tf32x3_kernel(const f
 
   if (wid < 4) {
     // ------------------------------------------------------------------ producers
+    // Warp w (< STAGES) owns ring slot w: it gathers all 128 rows of its (tap, chunk) uses — lane l takes rows
+    // l, l+32, l+64, l+96, i.e. 4 x CH independent 16-byte loads in flight per lane — so STAGES stages' worth of
+    // L2 gathers are in flight per CTA (two CTAs per SM).
     const int r = tid;
-    const uint32_t a_off = static_cast<uint32_t>((r >> 3) * 128 + (r & 7) * 16);
     int use = 0;
     for (int t = 0; t < K; ++t) {
       if (!((active >> t) & 1u)) continue;
-      const int src = s_nbr[r * K + t];
       for (int g = 0; g < C::G; ++g, ++use) {
-        const int s = use % C::STAGES;
-        const uint32_t ph = static_cast<uint32_t>((use / C::STAGES) & 1);
-        mbar_wait(smem_u32(&s_bar[4 + s]), ph ^ 1u);  // slot free (first pass returns at once)
-        uint8_t *st = stage_base + s * C::STAGE;
-        if (tid == 0) {
-          const uint32_t bytes = 2u * C::B_TILE;
-          mbar_arrive_expect_tx(smem_u32(&s_bar[s]), bytes);
-          bulk_g2s(smem_u32(st + 2 * C::A_TILE), packed_w + (static_cast<size_t>(t) * C::G + g) * (2 * C::KC * COUT),
-                   bytes, smem_u32(&s_bar[s]));
+        // Producer warp w owns ring slot w exclusively (uses u = w mod STAGES): with one warp per slot a warp can
+        // never run a full mbarrier phase ahead of the tensor core, so the parity waits cannot alias.
+        const int s = use % C::SA;
+        if (s != wid) continue;
+        const uint32_t ph = static_cast<uint32_t>((use / C::SA) & 1);
+        // lane l gathers rows l, l+32, l+64, l+96 (4 x 64 contiguous bytes): 16 independent 16-byte loads in flight
+        float4 v[4][C::CH];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int src = s_nbr[(lane + 32 * q) * K + t];
+          if (src >= 0) {
+            const float4 *p = reinterpret_cast<const float4 *>(in + static_cast<size_t>(src) * CIN + g * C::KC);
+#pragma unroll
+            for (int c = 0; c < C::CH; ++c) v[q][c] = __ldg(p + c);
+          } else {
+#pragma unroll
+            for (int c = 0; c < C::CH; ++c) v[q][c] = make_float4(0.f, 0.f, 0.f, 0.f);
+          }
         }
-        float4 v[C::CH];
-        if (src >= 0) {
-          const float4 *p = reinterpret_cast<const float4 *>(in + static_cast<size_t>(src) * CIN + g * C::KC);
+        mbar_wait(smem_u32(&s_bar[kAE + s]), ph ^ 1u);  // slot free (first pass returns at once)
+        uint8_t *st = a_base + s * C::A_STAGE;
+        // A-tile layout: k-chunk c at c*2048 (LBO), 8-row groups 128 B apart (SBO): the 32 lanes of one store
+        // instruction (32 consecutive rows, same chunk) cover 512 contiguous bytes — no bank conflicts.
 #pragma unroll
-          for (int c = 0; c < C::CH; ++c) v[c] = __ldg(p + c);
-        } else {
+        for (int q = 0; q < 4; ++q) {
+          const int row = lane + 32 * q;
+          const uint32_t a_off = static_cast<uint32_t>((row >> 3) * 128 + (row & 7) * 16);
 #pragma unroll
-          for (int c = 0; c < C::CH; ++c) v[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-        }
-#pragma unroll
-        for (int c = 0; c < C::CH; ++c) {
-          float4 h, l;
-          split_tf32(v[c].x, h.x, l.x);
-          split_tf32(v[c].y, h.y, l.y);
-          split_tf32(v[c].z, h.z, l.z);
-          split_tf32(v[c].w, h.w, l.w);
-          *reinterpret_cast<float4 *>(st + c * (kM * 16) + a_off) = h;
-          *reinterpret_cast<float4 *>(st + C::A_TILE + c * (kM * 16) + a_off) = l;
+          for (int c = 0; c < C::CH; ++c) {
+            float4 h, l;
+            split_tf32(v[q][c].x, h.x, l.x);
+            split_tf32(v[q][c].y, h.y, l.y);
+            split_tf32(v[q][c].z, h.z, l.z);
+            split_tf32(v[q][c].w, h.w, l.w);
+            *reinterpret_cast<float4 *>(st + c * (kM * 16) + a_off) = h;
+            *reinterpret_cast<float4 *>(st + C::A_TILE + c * (kM * 16) + a_off) = l;
+          }
         }
         fence_proxy_async();
-        mbar_arrive(smem_u32(&s_bar[s]));
+        mbar_arrive(smem_u32(&s_bar[kAF + s]));
       }
     }
     // ------------------------------------------------------------------ epilogue
-    mbar_wait(smem_u32(&s_bar[8]), 0u);
+    mbar_wait(smem_u32(&s_bar[kTF]), 0u);
     tc_fence_after();
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(wid * 32) << 16);
     const bool live = r < rows;
@@ -238,13 +261,23 @@ __global__ void __launch_bounds__(kThreads, 1) gather_gemm_tf32x3_kernel(const f
         for (int j = 0; j < 16; ++j) a[j] = 0u;
       }
       if (live) {
-        float o[16];
+        float o[16], res[16];
+        if (rrow) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            const float4 rv = __ldg(reinterpret_cast<const float4 *>(rrow + c0 + j));
+            res[j] = rv.x;
+            res[j + 1] = rv.y;
+            res[j + 2] = rv.z;
+            res[j + 3] = rv.w;
+          }
+        }
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
           float v = __uint_as_float(a[j]);
           if (scale) v = v * __ldg(scale + c0 + j);
           if (shift) v = v + __ldg(shift + c0 + j);
-          if (rrow) v = v + rrow[c0 + j];
+          if (rrow) v = v + res[j];
           if (relu) v = fmaxf(v, 0.f);
           o[j] = v;
         }
@@ -254,19 +287,19 @@ __global__ void __launch_bounds__(kThreads, 1) gather_gemm_tf32x3_kernel(const f
       }
     }
     tc_fence_before();
-  } else {
+  } else if (wid == 4) {
     // ------------------------------------------------------------------ MMA issuer (warp 4)
     if (n_stage_uses == 0) {
-      if (lane == 0) mbar_arrive(smem_u32(&s_bar[8]));
+      if (lane == 0) mbar_arrive(smem_u32(&s_bar[kTF]));
     } else {
       for (int use = 0; use < n_stage_uses; ++use) {
-        const int s = use % C::STAGES;
-        const uint32_t ph = static_cast<uint32_t>((use / C::STAGES) & 1);
-        mbar_wait(smem_u32(&s_bar[s]), ph);
+        const int sa = use % C::SA, sb = use % C::SB;
+        mbar_wait(smem_u32(&s_bar[kBF + sb]), static_cast<uint32_t>((use / C::SB) & 1));
+        mbar_wait(smem_u32(&s_bar[kAF + sa]), static_cast<uint32_t>((use / C::SA) & 1));
         tc_fence_after();
         if (lane == 0) {
-          const uint32_t st = smem_u32(stage_base + s * C::STAGE);
-          const uint32_t a_hi = st, a_lo = st + C::A_TILE, b_hi = st + 2 * C::A_TILE, b_lo = b_hi + C::B_TILE;
+          const uint32_t a_hi = smem_u32(a_base + sa * C::A_STAGE), a_lo = a_hi + C::A_TILE;
+          const uint32_t b_hi = smem_u32(b_base + sb * C::B_STAGE), b_lo = b_hi + C::B_TILE;
 #pragma unroll
           for (int j = 0; j < C::KC / 8; ++j) {
             const uint32_t ao = static_cast<uint32_t>(2 * j) * (kM * 16), bo = static_cast<uint32_t>(2 * j) * (COUT * 16);
@@ -276,13 +309,29 @@ __global__ void __launch_bounds__(kThreads, 1) gather_gemm_tf32x3_kernel(const f
             umma_tf32(tmem_base, dah, dbl, C::IDESC, 1u);
             umma_tf32(tmem_base, dah, dbh, C::IDESC, 1u);
           }
-          umma_commit(smem_u32(&s_bar[4 + s]));                               // stage back to the producers
-          if (use == n_stage_uses - 1) umma_commit(smem_u32(&s_bar[8]));      // accumulator ready
+          umma_commit(smem_u32(&s_bar[kAE + sa]));                             // gathered rows consumed
+          umma_commit(smem_u32(&s_bar[kBE + sb]));                             // weights consumed
+          if (use == n_stage_uses - 1) umma_commit(smem_u32(&s_bar[kTF]));    // accumulator ready
         }
         __syncwarp();
       }
     }
     tc_fence_before();
+  } else {
+    // ------------------------------------------------------------------ weight TMA (warp 5, one lane)
+    if (lane == 0) {
+      int use = 0;
+      for (int t = 0; t < K; ++t) {
+        if (!((active >> t) & 1u)) continue;
+        for (int g = 0; g < C::G; ++g, ++use) {
+          const int sb = use % C::SB;
+          mbar_wait(smem_u32(&s_bar[kBE + sb]), static_cast<uint32_t>((use / C::SB) & 1) ^ 1u);
+          mbar_arrive_expect_tx(smem_u32(&s_bar[kBF + sb]), static_cast<uint32_t>(C::B_STAGE));
+          bulk_g2s(smem_u32(b_base + sb * C::B_STAGE), packed_w + (static_cast<size_t>(t) * C::G + g) * (2 * C::KC * COUT),
+                   static_cast<uint32_t>(C::B_STAGE), smem_u32(&s_bar[kBF + sb]));
+        }
+      }
+    }
   }
   __syncthreads();
   if (wid == 4) {
@@ -318,7 +367,7 @@ template <int CIN, int COUT>
 int launch(const float *in, const int32_t *nbr, const int32_t *n_out_dev, int64_t n_cap, int K, const float *packed,
            const float *scale, const float *shift, const float *residual, int relu, float *out, cudaStream_t st) {
   using C = Cfg<CIN, COUT>;
-  const size_t smem = static_cast<size_t>(C::STAGES) * C::STAGE + static_cast<size_t>(kM) * K * sizeof(int32_t) + 1024;
+  const size_t smem = static_cast<size_t>(C::RING_BYTES) + static_cast<size_t>(kM) * K * sizeof(int32_t) + 1024;
   if (smem > 227 * 1024) return P3D_ERR_UNSUPPORTED;
   auto kern = gather_gemm_tf32x3_kernel<CIN, COUT>;
   P3D_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
@@ -341,7 +390,7 @@ extern "C" size_t p3d_sparse_conv_packed_weight_bytes(int K, int Cin, int Cout) 
 extern "C" int p3d_sparse_conv_pack_weights(const float *weight, int K, int Cin, int Cout, float *packed,
                                             p3d_stream_t stream) {
   if (!weight || !packed || K < 1) return P3D_ERR_INVALID_ARG;
-  if (Cin < 16 || Cout < 16 || Cin % 16 || Cout % 16 || (Cin > 32 && Cin % 32)) return P3D_ERR_UNSUPPORTED;
+  if (Cin < 16 || Cout < 16 || Cin % 16 || Cout % 16 || false) return P3D_ERR_UNSUPPORTED;
   const long long total = static_cast<long long>(K) * Cin * Cout;
   tc::pack_weights_kernel<<<div_up(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(weight, K, Cin, Cout,
                                                                                             packed);

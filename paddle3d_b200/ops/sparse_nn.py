@@ -115,11 +115,23 @@ class _Pending:
     __slots__ = ("x", "nbr", "num", "cap", "K", "cin", "cout", "weight", "scale", "shift", "residual", "relu", "precision")
 
 
+PROFILE = None  # set to a list to record (cin, cout, K, precision, nbr, num, start_event, end_event) per conv launch
+
+
 def _run(p):
     xin = p.x.values()
     dev = xin.device
     out = torch.empty((p.cap, p.cout), dtype=torch.float32, device=dev)
     res = p.residual.values() if p.residual is not None else None
+    if PROFILE is not None:
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record(torch.cuda.current_stream(dev))
+        check(lib().p3d_sparse_conv_gather_gemm(ptr(xin), ptr(p.nbr), ptr(p.num), p.cap, p.K, p.cin, p.cout,
+                                                ptr(p.weight), ptr(p.scale), ptr(p.shift), ptr(res), int(p.relu),
+                                                int(p.precision), ptr(out), stream(dev)), "sparse_conv_gather_gemm")
+        e.record(torch.cuda.current_stream(dev))
+        PROFILE.append((p.cin, p.cout, p.K, p.precision, p.nbr, p.num, s, e))
+        return out
     check(lib().p3d_sparse_conv_gather_gemm(ptr(xin), ptr(p.nbr), ptr(p.num), p.cap, p.K, p.cin, p.cout,
                                             ptr(p.weight), ptr(p.scale), ptr(p.shift), ptr(res), int(p.relu),
                                             int(p.precision), ptr(out), stream(dev)), "sparse_conv_gather_gemm")
