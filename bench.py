@@ -205,15 +205,8 @@ def main():
     precision = sp.TF32X3 if args.precision == "tf32x3" else sp.FP32
     pipe = CenterPointHotPath(cfg, dev, precision=precision, seed=0)
     if world > 1:  # weights only: one broadcast over NVLink at start, no per-frame collective
-        for l in pipe.net.all_layers():
-            for name in ("weight", "bias", "_mean", "_variance"):
-                t = getattr(l, name, None)
-                if isinstance(t, torch.Tensor):
-                    dist.broadcast(t, 0)
-        for l in pipe.net.all_layers():
-            if isinstance(l, sp.BatchNorm):
-                l._bias_fold.clear()
-                l.set_parameters(l.weight, l.bias, l._mean, l._variance)
+        from paddle3d_b200.sharding import broadcast_weights
+        broadcast_weights(pipe.net, 0)
     # frames: rank r owns frames r, r + world, ... of the sweep (frame-parallel sharding)
     frames = frame_pool(cfg, POOL, seed0=rank * 100)
     dev_frames = [torch.from_numpy(f).to(dev) for f in frames]

@@ -8,6 +8,8 @@
 //   paddle3d/ops/voxel/voxelize_op.cc        (Tensor::shape/data/size/type/is_cpu, empty, full,
 //                                             PD_DISPATCH_FLOATING_TYPES, PD_THROW, PD_BUILD_OP chain)
 //   paddle3d/ops/iou3d_nms/iou3d_cpu.cpp     (Tensor::shape/data, empty)
+// It also carries the few extra spellings paddle_ext/p3d_paddle_ops.cc needs for its compile check
+// (UINT8, Tensor::stream/copy_to, experimental::slice) as no-op stand-ins.
 // Tensors are host-only, ref-counted byte buffers.  Nothing here is a port of
 // Paddle code; it is an independent shim with the same spelling.
 #pragma once
@@ -24,7 +26,7 @@
 
 namespace paddle {
 
-enum class DataType { BOOL, INT32, INT64, FLOAT32, FLOAT64 };
+enum class DataType { BOOL, UINT8, INT32, INT64, FLOAT32, FLOAT64 };
 
 struct CPUPlace {};
 struct GPUPlace {};
@@ -32,6 +34,7 @@ struct GPUPlace {};
 inline size_t p3d_stub_sizeof(DataType t) {
   switch (t) {
     case DataType::BOOL: return 1;
+    case DataType::UINT8: return 1;
     case DataType::INT32: return 4;
     case DataType::INT64: return 8;
     case DataType::FLOAT32: return 4;
@@ -67,6 +70,10 @@ class Tensor {
   bool is_gpu_pinned() const { return false; }
   template <typename T>
   T* data() const { return reinterpret_cast<T*>(buf_.get()); }
+  // compile-check-only surface used by paddle_ext/ (never executed in this repo)
+  void* stream() const { return nullptr; }
+  template <typename P>
+  Tensor copy_to(P, bool) const { return *this; }
 
  private:
   std::vector<int64_t> shape_;
@@ -88,6 +95,7 @@ inline Tensor full(std::vector<int64_t> shape, V value, DataType dtype, P) {
   int64_t n = t.size();
   switch (dtype) {
     case DataType::BOOL: { auto* p = t.data<bool>(); for (int64_t i = 0; i < n; ++i) p[i] = value != 0; break; }
+    case DataType::UINT8: { auto* p = t.data<uint8_t>(); for (int64_t i = 0; i < n; ++i) p[i] = static_cast<uint8_t>(value); break; }
     case DataType::INT32: { auto* p = t.data<int32_t>(); for (int64_t i = 0; i < n; ++i) p[i] = static_cast<int32_t>(value); break; }
     case DataType::INT64: { auto* p = t.data<int64_t>(); for (int64_t i = 0; i < n; ++i) p[i] = static_cast<int64_t>(value); break; }
     case DataType::FLOAT32: { auto* p = t.data<float>(); for (int64_t i = 0; i < n; ++i) p[i] = static_cast<float>(value); break; }
@@ -113,6 +121,11 @@ struct OpStubBuilder {
   OpStubBuilder& Attrs(std::initializer_list<std::string>) { return *this; }
 };
 inline std::string Vec(const std::string& s) { return s + "@VECTOR"; }
+
+namespace experimental {
+inline Tensor slice(const Tensor& x, std::vector<int64_t>, std::vector<int64_t>, std::vector<int64_t>, std::vector<int64_t>,
+                    std::vector<int64_t>) { return x; }
+}  // namespace experimental
 
 }  // namespace paddle
 

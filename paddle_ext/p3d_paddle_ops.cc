@@ -1,0 +1,284 @@
+// Paddle custom-op glue: the SAME registrations (op names, inputs, outputs, attrs, infer functions) as the
+// reference's hot-path ops, with kernel functions that call the C ABI of libp3d_b200.so.
+//
+//   hard_voxelize            paddle3d/ops/voxel/voxelize_op.cc:183-191
+//   boxes_iou_bev_gpu, boxes_overlap_bev_gpu, nms_gpu, nms_normal_gpu
+//                            paddle3d/ops/iou3d_nms/iou3d_nms_api.cpp:73-108
+//   centerpoint_postprocess  paddle3d/ops/centerpoint_postprocess/postprocess.cc:91-104
+//   bev_pool_v2              paddle3d/ops/bev_pool_v2/bev_pool.cc:111-118
+//   bev_pool_v2_bkwd         paddle3d/ops/bev_pool_v2_backward/bev_pool_bkwd.cc:75-80
+//
+// Build (where PaddlePaddle exists): list this file as the `sources` of the op in paddle3d/ops/__init__.py and
+// add  extra_ldflags=['-L<repo>/paddle3d_b200', '-lp3d_b200']  — see INTEGRATION.md.  In this repository
+// PaddlePaddle is not installable, so the file is compile-checked against oracle/stub/paddle/extension.h
+// (tests/test_abi.py::test_paddle_glue_compiles) and the C ABI itself is exercised through ctypes.
+#include <vector>
+
+#include "paddle/extension.h"
+#include "p3d_b200.h"
+
+#define P3D_CHECK_GPU(x) PD_CHECK((x).is_gpu() || (x).is_gpu_pinned(), #x " must be a GPU Tensor.")
+#define P3D_CALL(expr)                                                                 \
+  do {                                                                                 \
+    int _rc = (expr);                                                                  \
+    if (_rc != 0) PD_THROW(std::string(#expr " failed: ") + p3d_status_string(_rc)); \
+  } while (0)
+
+namespace {
+
+paddle::Tensor workspace(size_t bytes) {
+  return paddle::empty({static_cast<int64_t>(bytes ? bytes : 256)}, paddle::DataType::UINT8, paddle::GPUPlace());
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------- hard_voxelize
+std::vector<paddle::Tensor> hard_voxelize(const paddle::Tensor &points, const std::vector<float> &voxel_size,
+                                          const std::vector<float> &point_cloud_range,
+                                          const int max_num_points_in_voxel, const int max_voxels) {
+  P3D_CHECK_GPU(points);  // this build has no CPUPlace kernel: the reference's CPU branch (voxelize_op.cc:153-155) throws here
+  const int64_t n = points.shape()[0];
+  const int f = static_cast<int>(points.shape()[1]);
+  auto voxels = paddle::empty({max_voxels, max_num_points_in_voxel, f}, paddle::DataType::FLOAT32, paddle::GPUPlace());
+  auto coords = paddle::empty({max_voxels, 3}, paddle::DataType::INT32, paddle::GPUPlace());
+  auto npv = paddle::empty({max_voxels}, paddle::DataType::INT32, paddle::GPUPlace());
+  auto num_voxels = paddle::empty({1}, paddle::DataType::INT32, paddle::GPUPlace());
+  const size_t ws_bytes = p3d_hard_voxelize_workspace_bytes(n, max_num_points_in_voxel, max_voxels);
+  auto ws = workspace(ws_bytes);
+  P3D_CALL(p3d_hard_voxelize(points.data<float>(), n, f, voxel_size.data(), point_cloud_range.data(),
+                             max_num_points_in_voxel, max_voxels, voxels.data<float>(), coords.data<int>(),
+                             npv.data<int>(), num_voxels.data<int>(), ws.data<uint8_t>(), ws_bytes, points.stream()));
+  return {voxels, coords, npv, num_voxels};
+}
+
+std::vector<std::vector<int64_t>> HardInferShape(std::vector<int64_t> points_shape, const std::vector<float> &voxel_size,
+                                                 const std::vector<float> &point_cloud_range,
+                                                 const int &max_num_points_in_voxel, const int &max_voxels) {
+  return {{max_voxels, max_num_points_in_voxel, points_shape[1]}, {max_voxels, 3}, {max_voxels}, {1}};
+}
+
+std::vector<paddle::DataType> HardInferDtype(paddle::DataType points_dtype) {
+  return {points_dtype, paddle::DataType::INT32, paddle::DataType::INT32, paddle::DataType::INT32};
+}
+
+PD_BUILD_OP(hard_voxelize)
+    .Inputs({"POINTS"})
+    .Outputs({"VOXELS", "COORS", "NUM_POINTS_PER_VOXEL", "num_voxels"})
+    .SetKernelFn(PD_KERNEL(hard_voxelize))
+    .Attrs({"voxel_size: std::vector<float>", "point_cloud_range: std::vector<float>", "max_num_points_in_voxel: int",
+            "max_voxels: int"})
+    .SetInferShapeFn(PD_INFER_SHAPE(HardInferShape))
+    .SetInferDtypeFn(PD_INFER_DTYPE(HardInferDtype));
+
+// ---------------------------------------------------------------- iou3d_nms
+static std::vector<paddle::Tensor> pairwise(const paddle::Tensor &a, const paddle::Tensor &b, bool iou) {
+  P3D_CHECK_GPU(a);
+  P3D_CHECK_GPU(b);
+  const int na = static_cast<int>(a.shape()[0]), nb = static_cast<int>(b.shape()[0]);
+  auto out = paddle::empty({na, nb}, paddle::DataType::FLOAT32, paddle::GPUPlace());
+  if (iou)
+    P3D_CALL(p3d_boxes_iou_bev(a.data<float>(), na, b.data<float>(), nb, out.data<float>(), a.stream()));
+  else
+    P3D_CALL(p3d_boxes_overlap_bev(a.data<float>(), na, b.data<float>(), nb, out.data<float>(), a.stream()));
+  return {out};
+}
+std::vector<paddle::Tensor> boxes_iou_bev_gpu(const paddle::Tensor &a, const paddle::Tensor &b) { return pairwise(a, b, true); }
+std::vector<paddle::Tensor> boxes_overlap_bev_gpu(const paddle::Tensor &a, const paddle::Tensor &b) {
+  return pairwise(a, b, false);
+}
+
+static std::vector<paddle::Tensor> nms_any(const paddle::Tensor &boxes, float thresh, int normal) {
+  P3D_CHECK_GPU(boxes);
+  const int n = static_cast<int>(boxes.shape()[0]);
+  auto keep_dev = paddle::empty({n > 0 ? n : 1}, paddle::DataType::INT32, paddle::GPUPlace());
+  auto num_dev = paddle::empty({1}, paddle::DataType::INT32, paddle::GPUPlace());
+  const size_t ws_bytes = p3d_nms_workspace_bytes(n);
+  auto ws = workspace(ws_bytes);
+  P3D_CALL(p3d_nms(boxes.data<float>(), n, thresh, normal, keep_dev.data<int>(), num_dev.data<int>(),
+                   ws.data<uint8_t>(), ws_bytes, boxes.stream()));
+  // the reference returns CPU tensors (iou3d_nms.cpp:89-92); one blocking copy of the result, none of the matrix
+  return {keep_dev.copy_to(paddle::CPUPlace(), true), num_dev.copy_to(paddle::CPUPlace(), true)};
+}
+std::vector<paddle::Tensor> nms_gpu(const paddle::Tensor &boxes, float nms_overlap_thresh) {
+  return nms_any(boxes, nms_overlap_thresh, 0);
+}
+std::vector<paddle::Tensor> nms_normal_gpu(const paddle::Tensor &boxes, float nms_overlap_thresh) {
+  return nms_any(boxes, nms_overlap_thresh, 1);
+}
+
+std::vector<paddle::DataType> PairInferDtype(paddle::DataType a, paddle::DataType b) { return {a}; }
+std::vector<std::vector<int64_t>> PairInferShape(std::vector<int64_t> a, std::vector<int64_t> b) { return {{a[0], b[0]}}; }
+std::vector<paddle::DataType> NmsInferDtype(paddle::DataType boxes_dtype) {
+  return {paddle::DataType::INT64, paddle::DataType::INT64};  // as declared by the reference (api.cpp:34-36)
+}
+std::vector<std::vector<int64_t>> NmsInferShape(std::vector<int64_t> boxes_shape) { return {{boxes_shape[0]}, {1}}; }
+
+PD_BUILD_OP(boxes_iou_bev_gpu)
+    .Inputs({"boxes_a_tensor", " boxes_b_tensor"})
+    .Outputs({"ans_iou_tensor"})
+    .SetKernelFn(PD_KERNEL(boxes_iou_bev_gpu))
+    .SetInferDtypeFn(PD_INFER_DTYPE(PairInferDtype))
+    .SetInferShapeFn(PD_INFER_SHAPE(PairInferShape));
+PD_BUILD_OP(boxes_overlap_bev_gpu)
+    .Inputs({"boxes_a", " boxes_b"})
+    .Outputs({"ans_overlap"})
+    .SetKernelFn(PD_KERNEL(boxes_overlap_bev_gpu))
+    .SetInferDtypeFn(PD_INFER_DTYPE(PairInferDtype))
+    .SetInferShapeFn(PD_INFER_SHAPE(PairInferShape));
+PD_BUILD_OP(nms_gpu)
+    .Inputs({"boxes"})
+    .Outputs({"keep", "num_to_keep"})
+    .Attrs({"nms_overlap_thresh: float"})
+    .SetKernelFn(PD_KERNEL(nms_gpu))
+    .SetInferDtypeFn(PD_INFER_DTYPE(NmsInferDtype))
+    .SetInferShapeFn(PD_INFER_SHAPE(NmsInferShape));
+PD_BUILD_OP(nms_normal_gpu)
+    .Inputs({"boxes"})
+    .Outputs({"keep", "num_to_keep"})
+    .Attrs({"nms_overlap_thresh: float"})
+    .SetKernelFn(PD_KERNEL(nms_normal_gpu))
+    .SetInferDtypeFn(PD_INFER_DTYPE(NmsInferDtype))
+    .SetInferShapeFn(PD_INFER_SHAPE(NmsInferShape));
+
+// ---------------------------------------------------------------- centerpoint_postprocess
+std::vector<paddle::Tensor> centerpoint_postprocess(
+    const std::vector<paddle::Tensor> &hm, const std::vector<paddle::Tensor> &reg,
+    const std::vector<paddle::Tensor> &height, const std::vector<paddle::Tensor> &dim,
+    const std::vector<paddle::Tensor> &vel, const std::vector<paddle::Tensor> &rot, const std::vector<float> &voxel_size,
+    const std::vector<float> &point_cloud_range, const std::vector<float> &post_center_range,
+    const std::vector<int> &num_classes, const int down_ratio, const float score_threshold,
+    const float nms_iou_threshold, const int nms_pre_max_size, const int nms_post_max_size, const bool with_velocity) {
+  if (!hm[0].is_gpu()) PD_THROW("Unsupported device type for centerpoint postprocess operator.");
+  PD_CHECK(hm[0].shape()[0] == 1, "hm[0] batch size must be 1.");
+  const int T = static_cast<int>(hm.size());
+  const int H = static_cast<int>(hm[0].shape()[2]), W = static_cast<int>(hm[0].shape()[3]);
+  std::vector<const float *> p[6];
+  std::vector<int32_t> hm_c(T);
+  const std::vector<paddle::Tensor> *lists[6] = {&hm, &reg, &height, &dim, &vel, &rot};
+  for (int k = 0; k < 6; ++k)
+    for (int t = 0; t < T; ++t) p[k].push_back((*lists[k])[t].data<float>());
+  for (int t = 0; t < T; ++t) hm_c[t] = static_cast<int32_t>(hm[t].shape()[1]);
+  const int dims = with_velocity ? 9 : 7;
+  const int rows = T * (nms_post_max_size > 1 ? nms_post_max_size : 1);
+  auto bboxes = paddle::empty({rows, dims}, paddle::DataType::FLOAT32, paddle::GPUPlace());
+  auto scores = paddle::empty({rows}, paddle::DataType::FLOAT32, paddle::GPUPlace());
+  auto labels = paddle::empty({rows}, paddle::DataType::INT64, paddle::GPUPlace());
+  auto counts = paddle::empty({T + 1}, paddle::DataType::INT32, paddle::GPUPlace());
+  const size_t ws_bytes = p3d_centerpoint_postprocess_workspace_bytes(T, H, W, nms_pre_max_size, nms_post_max_size);
+  auto ws = workspace(ws_bytes);
+  P3D_CALL(p3d_centerpoint_postprocess(T, p[0].data(), hm_c.data(), p[1].data(), p[2].data(), p[3].data(), p[4].data(),
+                                       p[5].data(), H, W, voxel_size.data(), point_cloud_range.data(),
+                                       post_center_range.data(), num_classes.data(), down_ratio, score_threshold,
+                                       nms_iou_threshold, nms_pre_max_size, nms_post_max_size, with_velocity ? 1 : 0,
+                                       bboxes.data<float>(), scores.data<float>(), labels.data<int64_t>(),
+                                       counts.data<int>(), ws.data<uint8_t>(), ws_bytes, hm[0].stream()));
+  // the op's outputs have data-dependent shape {-1, 9|7}: one scalar read gives K, then slice
+  const int k = counts.copy_to(paddle::CPUPlace(), true).data<int>()[T];
+  return {paddle::experimental::slice(bboxes, {0}, {0}, {k}, {}, {}), paddle::experimental::slice(scores, {0}, {0}, {k}, {}, {}),
+          paddle::experimental::slice(labels, {0}, {0}, {k}, {}, {})};
+}
+
+std::vector<std::vector<int64_t>> PostProcessInferShape(
+    const std::vector<std::vector<int64_t>> &hm_shape, const std::vector<std::vector<int64_t>> &reg_shape,
+    const std::vector<std::vector<int64_t>> &height_shape, const std::vector<std::vector<int64_t>> &dim_shape,
+    const std::vector<std::vector<int64_t>> &vel_shape, const std::vector<std::vector<int64_t>> &rot_shape,
+    const std::vector<float> &voxel_size, const std::vector<float> &point_cloud_range,
+    const std::vector<float> &post_center_range, const std::vector<int> &num_classes, const int down_ratio,
+    const float score_threshold, const float nms_iou_threshold, const int nms_pre_max_size,
+    const int nms_post_max_size, const bool with_velocity) {
+  if (with_velocity) return {{-1, 9}, {-1}, {-1}};
+  return {{-1, 7}, {-1}, {-1}};
+}
+
+std::vector<paddle::DataType> PostProcessInferDtype(
+    const std::vector<paddle::DataType> &hm_dtype, const std::vector<paddle::DataType> &reg_dtype,
+    const std::vector<paddle::DataType> &height_dtype, const std::vector<paddle::DataType> &dim_dtype,
+    const std::vector<paddle::DataType> &vel_dtype, const std::vector<paddle::DataType> &rot_dtype) {
+  return {reg_dtype[0], hm_dtype[0], paddle::DataType::INT64};
+}
+
+PD_BUILD_OP(centerpoint_postprocess)
+    .Inputs({paddle::Vec("HM"), paddle::Vec("REG"), paddle::Vec("HEIGHT"), paddle::Vec("DIM"), paddle::Vec("VEL"),
+             paddle::Vec("ROT")})
+    .Outputs({"BBOXES", "SCORES", "LABELS"})
+    .SetKernelFn(PD_KERNEL(centerpoint_postprocess))
+    .Attrs({"voxel_size: std::vector<float>", "point_cloud_range: std::vector<float>",
+            "post_center_range: std::vector<float>", "num_classes: std::vector<int>", "down_ratio: int",
+            "score_threshold: float", "nms_iou_threshold: float", "nms_pre_max_size: int", "nms_post_max_size: int",
+            "with_velocity: bool"})
+    .SetInferShapeFn(PD_INFER_SHAPE(PostProcessInferShape))
+    .SetInferDtypeFn(PD_INFER_DTYPE(PostProcessInferDtype));
+
+// ---------------------------------------------------------------- bev_pool_v2 / bev_pool_v2_bkwd
+std::vector<paddle::Tensor> bev_pool_v2_forward(const paddle::Tensor &_depth, const paddle::Tensor &_feat,
+                                                const paddle::Tensor &_ranks_depth, const paddle::Tensor &_ranks_feat,
+                                                const paddle::Tensor &_ranks_bev, const paddle::Tensor &_interval_lengths,
+                                                const paddle::Tensor &_interval_starts,
+                                                const std::vector<int> &_bev_feat_shape) {
+  P3D_CHECK_GPU(_feat);
+  const int c = static_cast<int>(_feat.shape()[3]);
+  const int n_intervals = static_cast<int>(_interval_lengths.shape()[0]);
+  std::vector<int64_t> shape(_bev_feat_shape.begin(), _bev_feat_shape.end());
+  auto out = paddle::empty(shape, _feat.type(), paddle::GPUPlace());  // zero-filled by the kernel's own memset
+  P3D_CALL(p3d_bev_pool_v2(_depth.data<float>(), _feat.data<float>(), _ranks_depth.data<int>(), _ranks_feat.data<int>(),
+                           _ranks_bev.data<int>(), _interval_lengths.data<int>(), _interval_starts.data<int>(),
+                           n_intervals, c, out.data<float>(), out.numel(), _feat.stream()));
+  return {out};
+}
+
+std::vector<paddle::Tensor> bev_pool_v2_backward(const paddle::Tensor &_out_grad, const paddle::Tensor &_depth,
+                                                 const paddle::Tensor &_feat, const paddle::Tensor &_ranks_depth,
+                                                 const paddle::Tensor &_ranks_feat, const paddle::Tensor &_ranks_bev,
+                                                 const paddle::Tensor &_interval_lengths,
+                                                 const paddle::Tensor &_interval_starts) {
+  P3D_CHECK_GPU(_out_grad);
+  const int c = static_cast<int>(_out_grad.shape()[3]);
+  const int n_intervals = static_cast<int>(_interval_lengths.shape()[0]);
+  auto depth_grad = paddle::empty(_depth.shape(), _depth.type(), paddle::GPUPlace());
+  auto feat_grad = paddle::empty(_feat.shape(), _feat.type(), paddle::GPUPlace());
+  P3D_CALL(p3d_bev_pool_v2_bkwd(_out_grad.data<float>(), _depth.data<float>(), _feat.data<float>(),
+                                _ranks_depth.data<int>(), _ranks_feat.data<int>(), _ranks_bev.data<int>(),
+                                _interval_lengths.data<int>(), _interval_starts.data<int>(), n_intervals, c,
+                                depth_grad.data<float>(), depth_grad.numel(), feat_grad.data<float>(), feat_grad.numel(),
+                                _out_grad.stream()));
+  return {depth_grad, feat_grad};
+}
+
+std::vector<std::vector<int64_t>> BevPoolV2InferShape(std::vector<int64_t> a, std::vector<int64_t> b, std::vector<int64_t> c,
+                                                      std::vector<int64_t> d, std::vector<int64_t> e, std::vector<int64_t> f,
+                                                      std::vector<int64_t> g, const std::vector<int> _bev_feat_shape) {
+  return {{_bev_feat_shape[0], _bev_feat_shape[1], _bev_feat_shape[2], _bev_feat_shape[3]}};
+}
+std::vector<paddle::DataType> BevPoolV2InferDtype(paddle::DataType a, paddle::DataType feat, paddle::DataType c,
+                                                  paddle::DataType d, paddle::DataType e, paddle::DataType f,
+                                                  paddle::DataType g) {
+  return {feat};
+}
+
+PD_BUILD_OP(bev_pool_v2)
+    .Inputs({"_depth", "_feat", "_ranks_depth", "_ranks_feat", "_ranks_bev", "_interval_lengths", "_interval_starts"})
+    .Attrs({"_bev_feat_shape: std::vector<int>"})
+    .Outputs({"out"})
+    .SetKernelFn(PD_KERNEL(bev_pool_v2_forward))
+    .SetInferShapeFn(PD_INFER_SHAPE(BevPoolV2InferShape))
+    .SetInferDtypeFn(PD_INFER_DTYPE(BevPoolV2InferDtype));
+
+std::vector<std::vector<int64_t>> BevPoolV2BkwdInferShape(std::vector<int64_t> og, std::vector<int64_t> depth,
+                                                          std::vector<int64_t> feat, std::vector<int64_t> d,
+                                                          std::vector<int64_t> e, std::vector<int64_t> f,
+                                                          std::vector<int64_t> g, std::vector<int64_t> h) {
+  return {depth, feat};
+}
+std::vector<paddle::DataType> BevPoolV2BkwdInferDtype(paddle::DataType og, paddle::DataType depth, paddle::DataType feat,
+                                                      paddle::DataType d, paddle::DataType e, paddle::DataType f,
+                                                      paddle::DataType g, paddle::DataType h) {
+  return {depth, feat};
+}
+
+PD_BUILD_OP(bev_pool_v2_bkwd)
+    .Inputs({"_out_grad", "_depth", "_feat", "_ranks_depth", "_ranks_feat", "_ranks_bev", "_interval_lengths",
+             "_interval_starts"})
+    .Outputs({"_depth_grad", "_feat_grad"})
+    .SetKernelFn(PD_KERNEL(bev_pool_v2_backward))
+    .SetInferShapeFn(PD_INFER_SHAPE(BevPoolV2BkwdInferShape))
+    .SetInferDtypeFn(PD_INFER_DTYPE(BevPoolV2BkwdInferDtype));

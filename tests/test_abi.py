@@ -65,3 +65,17 @@ def test_invalid_arguments_return_status_codes():
     rc = L.p3d_hard_voxelize(None, 0, 4, tiny, big, 4, 16, None, None, None, None, None, 0, None)
     assert rc == -4
     assert L.p3d_nms(None, -1, 0.5, 0, None, None, None, 0, None) == -1
+
+
+def test_paddle_glue_compiles():
+    """paddle_ext/p3d_paddle_ops.cc (the PD_BUILD_OP registrations that bind the C ABI under PaddlePaddle) must at
+    least compile against the stub extension header: PaddlePaddle itself is not installable here."""
+    import subprocess
+    r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-I", os.path.join(ROOT, "oracle", "stub"), "-I",
+                        os.path.join(ROOT, "include"), os.path.join(ROOT, "paddle_ext", "p3d_paddle_ops.cc")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    src = open(os.path.join(ROOT, "paddle_ext", "p3d_paddle_ops.cc")).read()
+    for op in ("hard_voxelize", "boxes_iou_bev_gpu", "boxes_overlap_bev_gpu", "nms_gpu", "nms_normal_gpu",
+               "centerpoint_postprocess", "bev_pool_v2", "bev_pool_v2_bkwd"):
+        assert "PD_BUILD_OP(%s)" % op in src
