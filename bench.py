@@ -175,7 +175,7 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--precision", default="tf32x3", choices=["fp32", "tf32x3"])
+    ap.add_argument("--precision", default="tf32x3", choices=["fp32", "tf32x3", "tf32x3_v1"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -202,7 +202,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     cfg = synth.C3
-    precision = sp.TF32X3 if args.precision == "tf32x3" else sp.FP32
+    precision = {"tf32x3": sp.TF32X3, "tf32x3_v1": sp.TF32X3_F32ROWS, "fp32": sp.FP32}[args.precision]
     pipe = CenterPointHotPath(cfg, dev, precision=precision, seed=0)
     if world > 1:  # weights only: one broadcast over NVLink at start, no per-frame collective
         from paddle3d_b200.sharding import broadcast_weights
@@ -307,10 +307,10 @@ def main():
             ms = s_ev.elapsed_time(e_ev)
             fl = 2.0 * pairs * cin * cout
             layers.append({"cin": cin, "cout": cout, "rows": rows, "pairs": pairs, "ms": round(ms, 4),
-                           "precision": "tf32x3" if prec == sp.TF32X3 else "fp32", "gflop": round(fl / 1e9, 3)})
+                           "precision": "tf32x3" if prec in (sp.TF32X3, sp.TF32X3_F32ROWS) else "fp32", "gflop": round(fl / 1e9, 3)})
             conv_ms += ms
             conv_flops += fl
-            if prec == sp.TF32X3:
+            if prec in (sp.TF32X3, sp.TF32X3_F32ROWS):
                 tc_ms += ms
                 tc_flops += fl
         extra["stage_ms_eager"] = stage

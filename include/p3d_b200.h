@@ -189,6 +189,24 @@ int p3d_sparse_conv_gather_gemm(const float *in, const int32_t *nbr, const int32
                                 const float *shift, const float *residual, int relu, int precision, float *out,
                                 p3d_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Split-row activations for the tensor-core path.  A "split" row tensor stores every row as its tf32 hi half
+ * followed by its tf32 lo half: [n][2][C] fp32 words (x ~= hi + lo, error <= 2^-22 |x|).  Keeping activations in
+ * this form between sparse-conv layers moves the 3xTF32 split out of the gather loop (paid once per produced
+ * element instead of once per gathering neighbour) and lets the kernel gather with cp.async.
+ *   p3d_rows_convert_layout: src_layout 0 = fp32 rows [n, C] -> split; 1 = split -> fp32 rows (hi + lo).
+ *   p3d_sparse_conv_gather_gemm_split: same contract as p3d_sparse_conv_gather_gemm(precision = TF32X3) with
+ *     in_split [n_in][2][Cin], residual_split [n_out][2][Cout] or NULL, packed weights
+ *     (p3d_sparse_conv_pack_weights), and out_f32 [n_out, Cout] and / or out_split [n_out][2][Cout] (either may be
+ *     NULL, not both).  Persistent grid sized to the device row count.
+ * ------------------------------------------------------------------------------------------- */
+int p3d_rows_convert_layout(const float *src, int src_layout, const int32_t *n_dev, int64_t n_cap, int C, float *dst,
+                            p3d_stream_t stream);
+int p3d_sparse_conv_gather_gemm_split(const float *in_split, const int32_t *nbr, const int32_t *n_out_dev,
+                                      int64_t n_out_cap, int K, int Cin, int Cout, const float *packed_weight,
+                                      const float *scale, const float *shift, const float *residual_split, int relu,
+                                      float *out_f32, float *out_split, p3d_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

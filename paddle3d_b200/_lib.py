@@ -45,6 +45,9 @@ SIGNATURES = {
     "p3d_sparse_affine_act": (_int, [_vp, _vp, _i64, _int, _vp, _vp, _vp, _int, _vp, _vp]),
     "p3d_sparse_conv_packed_weight_bytes": (_sz, [_int, _int, _int]),
     "p3d_sparse_conv_pack_weights": (_int, [_vp, _int, _int, _int, _vp, _vp]),
+    "p3d_rows_convert_layout": (_int, [_vp, _int, _vp, _i64, _int, _vp, _vp]),
+    "p3d_sparse_conv_gather_gemm_split": (_int, [_vp, _vp, _vp, _i64, _int, _int, _int, _vp, _vp, _vp, _vp, _int, _vp,
+                                                 _vp, _vp]),
     "p3d_sparse_conv_gather_gemm": (_int, [_vp, _vp, _vp, _i64, _int, _int, _int, _vp, _vp, _vp, _vp, _int, _int,
                                            _vp, _vp]),
 }

@@ -20,86 +20,10 @@
 // Taps that no row of the tile uses are skipped for the whole tile (block-uniform bitmask).
 // Weights are packed once per layer by p3d_sparse_conv_pack_weights into exactly the shared-memory image:
 //   packed[tap][chunk g][hi|lo][KC/4 k-chunks][Cout rows][4 floats].
-#include "common.cuh"
+#include "tc_common.cuh"
 
 namespace p3d {
 namespace tc {
-
-constexpr int kM = 128;
-constexpr int kProducers = 128;
-constexpr int kThreads = 192;  // 4 producer/epilogue warps + 1 MMA warp + 1 weight-TMA warp
-
-__host__ __device__ constexpr int kc_of(int cin) { return cin < 16 ? cin : 16; }  // channels per pipeline stage
-
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
-
-__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  const long long t0 = clock64();
-  uint32_t done;
-  do {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(done)
-        : "r"(bar), "r"(parity)
-        : "memory");
-    if (!done && clock64() - t0 > 4000000000ll) __trap();  // ~2 s: a protocol bug must not hang the GPU
-  } while (!done);
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
-               "l"(src), "r"(bytes), "r"(bar)
-               : "memory");
-}
-
-__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
-                                          uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-}
-
-// K-major, no swizzle: core matrix = 8 rows x 16 B contiguous; LBO = distance between the two 16-byte
-// K-chunks of one MMA (K = 8 tf32), SBO = distance between 8-row groups (cute::UMMA::SmemDescriptor).
-__device__ __forceinline__ uint64_t smem_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
-  uint64_t d = 0;
-  d |= static_cast<uint64_t>((addr & 0x3ffffu) >> 4);
-  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3fffu) << 16;
-  d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3fffu) << 32;
-  d |= 1ull << 46;  // descriptor version 1 (Blackwell)
-  return d;         // base_offset 0, lbo_mode 0, layout_type 0 = SWIZZLE_NONE
-}
-
-__device__ __forceinline__ void split_tf32(float x, float &hi, float &lo) {
-  uint32_t h;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(h) : "f"(x));
-  hi = __uint_as_float(h);
-  const float r = x - hi;  // exact in fp32
-  uint32_t l;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(l) : "f"(r));
-  lo = __uint_as_float(l);
-}
 
 template <int CIN, int COUT>
 struct Cfg {
@@ -116,7 +40,12 @@ struct Cfg {
   static constexpr int SB_RAW = (96 * 1024 - SA * A_STAGE) / B_STAGE;
   static constexpr int SB = SB_RAW > 8 ? 8 : SB_RAW;
   static constexpr int RING_BYTES = SA * A_STAGE + SB * B_STAGE;
-  static constexpr int TMEM_COLS = COUT < 32 ? 32 : COUT;
+  // Independent TMEM accumulators: back-to-back tcgen05.mma into ONE accumulator serialise on its dependency
+  // latency (~200 cycles each, measured), so the three 3xTF32 products go to separate column ranges and are summed
+  // in the epilogue.  Cout = 128 keeps two (256 columns) so that two CTAs still fit the 512 TMEM columns of an SM.
+  static constexpr int NACC = (COUT <= 64) ? 3 : 2;
+  static constexpr int TMEM_COLS = (NACC * COUT <= 32) ? 32 : (NACC * COUT <= 64) ? 64 : (NACC * COUT <= 128) ? 128
+                                   : (NACC * COUT <= 256) ? 256 : 512;
   static constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(COUT >> 3) << 17) |
                                     (static_cast<uint32_t>(kM >> 4) << 24);
   static_assert(CIN % 16 == 0 && COUT % 16 == 0 && COUT <= 256, "tensor-core path needs 16-channel multiples");
@@ -255,6 +184,19 @@ __global__ void __launch_bounds__(kThreads, 2) gather_gemm_tf32x3_kernel(const f
             : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]), "=r"(a[4]), "=r"(a[5]), "=r"(a[6]), "=r"(a[7]), "=r"(a[8]),
               "=r"(a[9]), "=r"(a[10]), "=r"(a[11]), "=r"(a[12]), "=r"(a[13]), "=r"(a[14]), "=r"(a[15])
             : "r"(taddr + static_cast<uint32_t>(c0)));
+#pragma unroll
+        for (int acc = 1; acc < C::NACC; ++acc) {
+          uint32_t b[16];
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, "
+              "%15}, [%16];"
+              : "=r"(b[0]), "=r"(b[1]), "=r"(b[2]), "=r"(b[3]), "=r"(b[4]), "=r"(b[5]), "=r"(b[6]), "=r"(b[7]), "=r"(b[8]),
+                "=r"(b[9]), "=r"(b[10]), "=r"(b[11]), "=r"(b[12]), "=r"(b[13]), "=r"(b[14]), "=r"(b[15])
+              : "r"(taddr + static_cast<uint32_t>(acc * COUT + c0)));
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+          for (int j = 0; j < 16; ++j) a[j] = __float_as_uint(__uint_as_float(a[j]) + __uint_as_float(b[j]));
+        }
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
       } else {
 #pragma unroll
@@ -305,9 +247,10 @@ __global__ void __launch_bounds__(kThreads, 2) gather_gemm_tf32x3_kernel(const f
             const uint32_t ao = static_cast<uint32_t>(2 * j) * (kM * 16), bo = static_cast<uint32_t>(2 * j) * (COUT * 16);
             const uint64_t dah = smem_desc(a_hi + ao, kM * 16, 128), dal = smem_desc(a_lo + ao, kM * 16, 128);
             const uint64_t dbh = smem_desc(b_hi + bo, COUT * 16, 128), dbl = smem_desc(b_lo + bo, COUT * 16, 128);
-            umma_tf32(tmem_base, dal, dbh, C::IDESC, (use | j) ? 1u : 0u);  // small terms first
-            umma_tf32(tmem_base, dah, dbl, C::IDESC, 1u);
-            umma_tf32(tmem_base, dah, dbh, C::IDESC, 1u);
+            const uint32_t first = (use | j) ? 1u : 0u;
+            umma_tf32(tmem_base, dal, dbh, C::IDESC, first);                               // acc 0
+            umma_tf32(tmem_base + (C::NACC == 3 ? COUT : 0), dah, dbl, C::IDESC, C::NACC == 3 ? first : 1u);  // acc 1 (or 0)
+            umma_tf32(tmem_base + (C::NACC - 1) * COUT, dah, dbh, C::IDESC, first);         // last acc
           }
           umma_commit(smem_u32(&s_bar[kAE + sa]));                             // gathered rows consumed
           umma_commit(smem_u32(&s_bar[kBE + sb]));                             // weights consumed

@@ -1,0 +1,391 @@
+// Sparse-conv gather-GEMM on tcgen05, version 2: activations travel between layers already split into their
+// tf32 hi / lo halves (row layout [n][2][C]: hi row, then lo row), so the 3xTF32 split is paid ONCE per produced
+// element (in the producing layer's epilogue) instead of once per gathering neighbour (11-27x), and the gather
+// becomes a pure copy that cp.async (LDGSTS, 16 B, zero-fill for missing neighbours) drops straight into the
+// canonical UMMA core-matrix tiles — no register staging, no ALU in the producer loop, many stages in flight.
+//
+//   grid      persistent: min(#tiles at capacity, 2 x SMs) CTAs, each walks tiles blockIdx.x, +gridDim.x, ...
+//             of the DEVICE row count (no empty CTAs for capacity-sized launches).
+//   warps 0-3 producers: per (tap, 16-channel chunk) use, 8 cp.async per thread (4 row groups x {hi, lo}); a warp
+//             instruction covers 8 rows x 64 contiguous bytes and lands on 512 contiguous bytes of shared memory
+//             (A tile: LBO = 128 B between k-chunks, SBO = 512 B between 8-row groups).  Completion is signalled
+//             with cp.async.mbarrier.arrive.noinc; producers run up to SA uses ahead.
+//   warp 5    weight TMA: cp.async.bulk of the packed [hi | lo] slice per use through its own, deeper ring.
+//   warp 4    MMA issuer: 3 tcgen05.mma.kind::tf32 per 8-wide k-step, tcgen05.commit back to both rings.
+//   warps 0-3 epilogue: tcgen05.ld, BN scale/shift (+bias), residual (= hi + lo of the split residual rows),
+//             ReLU, then either plain fp32 rows, split rows for the next layer, or both.
+#include "tc_common.cuh"
+
+namespace p3d {
+namespace tc2 {
+
+using namespace tc;
+
+template <int CIN, int COUT>
+struct Cfg {
+  static constexpr int KC = 16;                   // channels per pipeline use
+  static constexpr int G = CIN / KC;
+  static constexpr int A_TILE = KC * kM * 4;      // 8 KB, one of hi / lo
+  static constexpr int B_TILE = KC * COUT * 4;
+  static constexpr int A_STAGE = 2 * A_TILE;
+  static constexpr int B_STAGE = 2 * B_TILE;
+  static constexpr int SA = (COUT <= 64) ? 4 : 3;
+  static constexpr int SB_RAW = (96 * 1024 - SA * A_STAGE) / B_STAGE;
+  static constexpr int SB = SB_RAW > 8 ? 8 : SB_RAW;
+  static constexpr int RING_BYTES = SA * A_STAGE + SB * B_STAGE;
+  // Independent TMEM accumulators: back-to-back tcgen05.mma into ONE accumulator serialise on its dependency
+  // latency (~200 cycles each, measured), so the three 3xTF32 products go to separate column ranges and are summed
+  // in the epilogue.  Cout = 128 keeps two (256 columns) so that two CTAs still fit the 512 TMEM columns of an SM.
+  static constexpr int NACC = (COUT <= 64) ? 3 : 2;
+  static constexpr int TMEM_COLS = (NACC * COUT <= 32) ? 32 : (NACC * COUT <= 64) ? 64 : (NACC * COUT <= 128) ? 128
+                                   : (NACC * COUT <= 256) ? 256 : 512;
+  static constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(COUT >> 3) << 17) |
+                                    (static_cast<uint32_t>(kM >> 4) << 24);
+  static_assert(CIN % 16 == 0 && COUT % 16 == 0 && COUT <= 256, "tensor-core path needs 16-channel multiples");
+};
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, bool valid) {
+  const uint32_t sz = valid ? 16u : 0u;  // src-size 0 => 16 bytes of zeros
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
+}
+
+template <int CIN, int COUT>
+__global__ void __launch_bounds__(kThreads, 2) gather_gemm_split_kernel(const float *__restrict__ in_split,
+                                                                        const int32_t *__restrict__ nbr,
+                                                                        const int32_t *__restrict__ n_out_dev,
+                                                                        long long n_cap, int K,
+                                                                        const float *__restrict__ packed_w,
+                                                                        const float *__restrict__ scale,
+                                                                        const float *__restrict__ shift,
+                                                                        const float *__restrict__ residual_split,
+                                                                        int relu, float *__restrict__ out_f32,
+                                                                        float *__restrict__ out_split,
+                                                                        long long *__restrict__ dbg) {
+  // dbg (optional, CTA 0 only): per-use clock64 timeline, 8 slots per use:
+  //   0 producer(warp0): slot free   1 producer: cp.async issued   2 TMA: slot free   3 TMA: issued
+  //   4 MMA: weights landed          5 MMA: rows landed            6 MMA: issued + committed
+  using C = Cfg<CIN, COUT>;
+  const long long n = n_out_dev ? min(static_cast<long long>(n_out_dev[0]), n_cap) : n_cap;
+  if (static_cast<long long>(blockIdx.x) * kM >= n) return;
+
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t *a_base = smem;
+  uint8_t *b_base = smem + C::SA * C::A_STAGE;
+  int32_t *s_nbr = reinterpret_cast<int32_t *>(smem + C::RING_BYTES);  // [kM][K]
+  __shared__ __align__(8) unsigned long long s_bar[4 + 4 + 8 + 8 + 1];
+  constexpr int kAF = 0, kAE = 4, kBF = 8, kBE = 16, kTF = 24;
+  __shared__ uint32_t s_tmem_base;
+  __shared__ uint32_t s_active;
+
+  const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
+  if (tid == kProducers) {
+    for (int s = 0; s < C::SA; ++s) {
+      mbar_init(smem_u32(&s_bar[kAF + s]), kProducers);  // one cp.async-completion arrival per producer thread
+      mbar_init(smem_u32(&s_bar[kAE + s]), 1);
+    }
+    for (int s = 0; s < C::SB; ++s) {
+      mbar_init(smem_u32(&s_bar[kBF + s]), 1);
+      mbar_init(smem_u32(&s_bar[kBE + s]), 1);
+    }
+    mbar_init(smem_u32(&s_bar[kTF]), 1);
+    fence_mbar_init();
+  }
+  if (wid == 4) {
+    __syncwarp();
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)),
+                 "r"(static_cast<uint32_t>(C::TMEM_COLS))
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = s_tmem_base;
+
+  int use_base = 0;  // pipeline uses consumed by earlier tiles of this CTA (ring phases keep running)
+  int tile_it = 0;
+  for (long long tile = blockIdx.x; tile * kM < n; tile += gridDim.x, ++tile_it) {
+    const long long row0 = tile * kM;
+    const int rows = static_cast<int>(min(static_cast<long long>(kM), n - row0));
+    if (tid == 0) s_active = 0u;
+    __syncthreads();  // previous tile fully drained (epilogue done, s_nbr free)
+    {
+      uint32_t mine = 0u;
+      for (int q = tid; q < kM * K; q += kThreads) {
+        const int v = (q < rows * K) ? __ldg(nbr + row0 * K + q) : -1;
+        s_nbr[q] = v;
+        if (v >= 0) mine |= 1u << (q % K);
+      }
+      mine = __reduce_or_sync(0xffffffffu, mine);
+      if (lane == 0 && mine) atomicOr(&s_active, mine);
+    }
+    __syncthreads();
+    const uint32_t active = s_active;
+    const int n_uses = __popc(active) * C::G;
+
+    if (wid < 4) {
+      // ---------------------------------------------------------------- producers (cp.async gathers)
+      const int sub = lane >> 2, ch = lane & 3;
+      int use = use_base;
+      for (int t = 0; t < K; ++t) {
+        if (!((active >> t) & 1u)) continue;
+        int src[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) src[q] = s_nbr[(wid * 32 + q * 8 + sub) * K + t];
+        for (int g = 0; g < C::G; ++g, ++use) {
+          const int s = use % C::SA;
+          mbar_wait(smem_u32(&s_bar[kAE + s]), (static_cast<uint32_t>(use / C::SA) & 1u) ^ 1u);
+          if (dbg && blockIdx.x == 0 && tid == 0 && use < 512) dbg[use * 8 + 0] = clock64();
+          const uint32_t st = smem_u32(a_base + s * C::A_STAGE);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const bool ok = src[q] >= 0;
+            const float *p = in_split + (ok ? static_cast<size_t>(src[q]) * (2 * CIN) : 0) + g * C::KC + ch * 4;
+            const uint32_t d = st + static_cast<uint32_t>((wid * 4 + q) * 512 + ch * 128 + sub * 16);
+            cp_async16(d, p, ok);                         // hi
+            cp_async16(d + C::A_TILE, p + CIN, ok);       // lo
+          }
+          cp_async_arrive_noinc(smem_u32(&s_bar[kAF + s]));
+          if (dbg && blockIdx.x == 0 && tid == 0 && use < 512) dbg[use * 8 + 1] = clock64();
+        }
+      }
+      // ---------------------------------------------------------------- epilogue
+      mbar_wait(smem_u32(&s_bar[kTF]), static_cast<uint32_t>(tile_it & 1));
+      tc_fence_after();
+      const int r = tid;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(wid * 32) << 16);
+      const bool live = r < rows;
+      const size_t orow = static_cast<size_t>(row0 + r);
+#pragma unroll 1
+      for (int c0 = 0; c0 < COUT; c0 += 16) {
+        uint32_t a[16];
+        if (n_uses > 0) {
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, "
+              "%15}, [%16];"
+              : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]), "=r"(a[4]), "=r"(a[5]), "=r"(a[6]), "=r"(a[7]),
+                "=r"(a[8]), "=r"(a[9]), "=r"(a[10]), "=r"(a[11]), "=r"(a[12]), "=r"(a[13]), "=r"(a[14]), "=r"(a[15])
+              : "r"(taddr + static_cast<uint32_t>(c0)));
+#pragma unroll
+          for (int acc = 1; acc < C::NACC; ++acc) {
+            uint32_t b[16];
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, "
+                "%15}, [%16];"
+                : "=r"(b[0]), "=r"(b[1]), "=r"(b[2]), "=r"(b[3]), "=r"(b[4]), "=r"(b[5]), "=r"(b[6]), "=r"(b[7]),
+                  "=r"(b[8]), "=r"(b[9]), "=r"(b[10]), "=r"(b[11]), "=r"(b[12]), "=r"(b[13]), "=r"(b[14]), "=r"(b[15])
+                : "r"(taddr + static_cast<uint32_t>(acc * COUT + c0)));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < 16; ++j) a[j] = __float_as_uint(__uint_as_float(a[j]) + __uint_as_float(b[j]));
+          }
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) a[j] = 0u;
+        }
+        if (live) {
+          float o[16], res[16];
+          if (residual_split) {
+            const float4 *rh = reinterpret_cast<const float4 *>(residual_split + orow * (2 * COUT) + c0);
+            const float4 *rl = reinterpret_cast<const float4 *>(residual_split + orow * (2 * COUT) + COUT + c0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float4 h = __ldg(rh + j), l = __ldg(rl + j);
+              res[4 * j] = h.x + l.x;
+              res[4 * j + 1] = h.y + l.y;
+              res[4 * j + 2] = h.z + l.z;
+              res[4 * j + 3] = h.w + l.w;
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float v = __uint_as_float(a[j]);
+            if (scale) v = v * __ldg(scale + c0 + j);
+            if (shift) v = v + __ldg(shift + c0 + j);
+            if (residual_split) v = v + res[j];
+            if (relu) v = fmaxf(v, 0.f);
+            o[j] = v;
+          }
+          if (out_f32) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4)
+              *reinterpret_cast<float4 *>(out_f32 + orow * COUT + c0 + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+          }
+          if (out_split) {
+            float h[16], l[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) split_tf32(o[j], h[j], l[j]);
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+              *reinterpret_cast<float4 *>(out_split + orow * (2 * COUT) + c0 + j) = make_float4(h[j], h[j + 1], h[j + 2], h[j + 3]);
+              *reinterpret_cast<float4 *>(out_split + orow * (2 * COUT) + COUT + c0 + j) =
+                  make_float4(l[j], l[j + 1], l[j + 2], l[j + 3]);
+            }
+          }
+        }
+      }
+      tc_fence_before();
+    } else if (wid == 4) {
+      // ---------------------------------------------------------------- MMA issuer
+      if (n_uses == 0) {
+        if (lane == 0) mbar_arrive(smem_u32(&s_bar[kTF]));
+      } else {
+        for (int u = 0; u < n_uses; ++u) {
+          const int use = use_base + u;
+          const int sa = use % C::SA, sb = use % C::SB;
+          mbar_wait(smem_u32(&s_bar[kBF + sb]), static_cast<uint32_t>(use / C::SB) & 1u);
+          if (dbg && blockIdx.x == 0 && lane == 0 && use < 512) dbg[use * 8 + 4] = clock64();
+          mbar_wait(smem_u32(&s_bar[kAF + sa]), static_cast<uint32_t>(use / C::SA) & 1u);
+          if (dbg && blockIdx.x == 0 && lane == 0 && use < 512) dbg[use * 8 + 5] = clock64();
+          fence_proxy_async();  // cp.async (generic proxy) writes -> tensor-core (async proxy) reads
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t a_hi = smem_u32(a_base + sa * C::A_STAGE), a_lo = a_hi + C::A_TILE;
+            const uint32_t b_hi = smem_u32(b_base + sb * C::B_STAGE), b_lo = b_hi + C::B_TILE;
+#pragma unroll
+            for (int j = 0; j < C::KC / 8; ++j) {
+              const uint32_t ao = static_cast<uint32_t>(2 * j) * 128, bo = static_cast<uint32_t>(2 * j) * (COUT * 16);
+              const uint64_t dah = smem_desc(a_hi + ao, 128, 512), dal = smem_desc(a_lo + ao, 128, 512);
+              const uint64_t dbh = smem_desc(b_hi + bo, COUT * 16, 128), dbl = smem_desc(b_lo + bo, COUT * 16, 128);
+              const uint32_t first = (u | j) ? 1u : 0u;
+              umma_tf32(tmem_base, dal, dbh, C::IDESC, first);                               // acc 0
+              umma_tf32(tmem_base + (C::NACC == 3 ? COUT : 0), dah, dbl, C::IDESC, C::NACC == 3 ? first : 1u);
+              umma_tf32(tmem_base + (C::NACC - 1) * COUT, dah, dbh, C::IDESC, first);         // last acc
+            }
+            umma_commit(smem_u32(&s_bar[kAE + sa]));
+            umma_commit(smem_u32(&s_bar[kBE + sb]));
+            if (u == n_uses - 1) umma_commit(smem_u32(&s_bar[kTF]));
+            if (dbg && blockIdx.x == 0 && use < 512) dbg[use * 8 + 6] = clock64();
+          }
+          __syncwarp();
+        }
+      }
+      tc_fence_before();
+    } else {
+      // ---------------------------------------------------------------- weight TMA
+      if (lane == 0) {
+        int use = use_base;
+        for (int t = 0; t < K; ++t) {
+          if (!((active >> t) & 1u)) continue;
+          for (int g = 0; g < C::G; ++g, ++use) {
+            const int sb = use % C::SB;
+            mbar_wait(smem_u32(&s_bar[kBE + sb]), (static_cast<uint32_t>(use / C::SB) & 1u) ^ 1u);
+            if (dbg && blockIdx.x == 0 && use < 512) dbg[use * 8 + 2] = clock64();
+            mbar_arrive_expect_tx(smem_u32(&s_bar[kBF + sb]), static_cast<uint32_t>(C::B_STAGE));
+            bulk_g2s(smem_u32(b_base + sb * C::B_STAGE), packed_w + (static_cast<size_t>(t) * C::G + g) * (2 * C::KC * COUT),
+                     static_cast<uint32_t>(C::B_STAGE), smem_u32(&s_bar[kBF + sb]));
+            if (dbg && blockIdx.x == 0 && use < 512) dbg[use * 8 + 3] = clock64();
+          }
+        }
+      }
+    }
+    use_base += n_uses;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (wid == 4) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                 "r"(static_cast<uint32_t>(C::TMEM_COLS))
+                 : "memory");
+  }
+}
+
+template <int CIN, int COUT>
+int launch(const float *in_split, const int32_t *nbr, const int32_t *n_out_dev, int64_t n_cap, int K,
+           const float *packed, const float *scale, const float *shift, const float *residual_split, int relu,
+           float *out_f32, float *out_split, cudaStream_t st, long long *dbg = nullptr) {
+  using C = Cfg<CIN, COUT>;
+  const size_t smem = static_cast<size_t>(C::RING_BYTES) + static_cast<size_t>(kM) * K * sizeof(int32_t) + 1024;
+  if (smem > 227 * 1024) return P3D_ERR_UNSUPPORTED;
+  auto kern = gather_gemm_split_kernel<CIN, COUT>;
+  P3D_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  const long long tiles = (n_cap + kM - 1) / kM;
+  const unsigned int grid = static_cast<unsigned int>(tiles < 2 * kNumSMs ? tiles : 2 * kNumSMs);
+  kern<<<grid, kThreads, smem, st>>>(in_split, nbr, n_out_dev, n_cap, K, packed, scale, shift, residual_split, relu,
+                                     out_f32, out_split, dbg);
+  P3D_LAUNCH_CHECK();
+  return P3D_OK;
+}
+
+// rows [n, C] fp32 <-> split rows [n][2][C]
+__global__ void __launch_bounds__(256) rows_split_kernel(const float *__restrict__ x, const int32_t *__restrict__ n_dev,
+                                                         long long n_cap, int C, float *__restrict__ out_split) {
+  const long long n = n_dev ? min(static_cast<long long>(n_dev[0]), n_cap) : n_cap;
+  const long long q = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (q >= n * C) return;
+  const long long r = q / C;
+  const int c = static_cast<int>(q - r * C);
+  float h, l;
+  split_tf32(x[q], h, l);
+  out_split[r * 2 * C + c] = h;
+  out_split[r * 2 * C + C + c] = l;
+}
+__global__ void __launch_bounds__(256) rows_merge_kernel(const float *__restrict__ xs, const int32_t *__restrict__ n_dev,
+                                                         long long n_cap, int C, float *__restrict__ out) {
+  const long long n = n_dev ? min(static_cast<long long>(n_dev[0]), n_cap) : n_cap;
+  const long long q = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (q >= n * C) return;
+  const long long r = q / C;
+  const int c = static_cast<int>(q - r * C);
+  out[q] = xs[r * 2 * C + c] + xs[r * 2 * C + C + c];
+}
+
+}  // namespace tc2
+}  // namespace p3d
+
+using namespace p3d;
+
+extern "C" int p3d_rows_convert_layout(const float *src, int src_layout, const int32_t *n_dev, int64_t n_cap, int C,
+                                       float *dst, p3d_stream_t stream) {
+  if (n_cap < 0 || C < 1 || (n_cap && (!src || !dst)) || (src_layout != 0 && src_layout != 1)) return P3D_ERR_INVALID_ARG;
+  if (n_cap == 0) return P3D_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (src_layout == 0)
+    tc2::rows_split_kernel<<<div_up(n_cap * C, 256), 256, 0, st>>>(src, n_dev, n_cap, C, dst);
+  else
+    tc2::rows_merge_kernel<<<div_up(n_cap * C, 256), 256, 0, st>>>(src, n_dev, n_cap, C, dst);
+  P3D_LAUNCH_CHECK();
+  return P3D_OK;
+}
+
+extern "C" int p3d_sparse_conv_gather_gemm_split(const float *in_split, const int32_t *nbr, const int32_t *n_out_dev,
+                                                 int64_t n_out_cap, int K, int Cin, int Cout, const float *packed_weight,
+                                                 const float *scale, const float *shift, const float *residual_split,
+                                                 int relu, float *out_f32, float *out_split, p3d_stream_t stream) {
+  if (n_out_cap < 0 || K < 1 || K > 32 || !packed_weight || (!out_f32 && !out_split) || (n_out_cap && (!in_split || !nbr)))
+    return P3D_ERR_INVALID_ARG;
+  if (n_out_cap == 0) return P3D_OK;
+  if ((reinterpret_cast<uintptr_t>(in_split) & 15) || (reinterpret_cast<uintptr_t>(out_f32) & 15) ||
+      (reinterpret_cast<uintptr_t>(out_split) & 15) || (reinterpret_cast<uintptr_t>(packed_weight) & 15) ||
+      (reinterpret_cast<uintptr_t>(residual_split) & 15))
+    return P3D_ERR_INVALID_ARG;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define P3D_TC2_CASE(CI, CO)                                                                                        \
+  if (Cin == CI && Cout == CO)                                                                                      \
+    return tc2::launch<CI, CO>(in_split, nbr, n_out_dev, n_out_cap, K, packed_weight, scale, shift, residual_split, \
+                               relu, out_f32, out_split, st);
+  P3D_TC2_CASE(16, 16)
+  P3D_TC2_CASE(16, 32)
+  P3D_TC2_CASE(32, 32)
+  P3D_TC2_CASE(32, 64)
+  P3D_TC2_CASE(64, 64)
+  P3D_TC2_CASE(64, 128)
+  P3D_TC2_CASE(128, 128)
+#undef P3D_TC2_CASE
+  return P3D_ERR_UNSUPPORTED;
+}
+
+// Debug aid (not part of the public header): same launch as p3d_sparse_conv_gather_gemm_split for the 64 -> 64
+// configuration with a per-use clock64 timeline of CTA 0 written to dbg[512 * 8].
+extern "C" int p3d_debug_split_timeline_64(const float *in_split, const int32_t *nbr, const int32_t *n_out_dev,
+                                           int64_t n_out_cap, int K, const float *packed_weight, float *out_f32,
+                                           long long *dbg, p3d_stream_t stream) {
+  return tc2::launch<64, 64>(in_split, nbr, n_out_dev, n_out_cap, K, packed_weight, nullptr, nullptr, nullptr, 0, out_f32,
+                             nullptr, static_cast<cudaStream_t>(stream), dbg);
+}

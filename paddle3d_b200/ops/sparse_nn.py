@@ -24,7 +24,8 @@ from .._lib import check, host_ints, lib
 from .._mem import ptr, require_cuda, stream, workspace
 from . import pillar_scatter as _ps
 
-FP32, TF32X3 = 0, 1
+FP32, TF32X3, TF32X3_F32ROWS = 0, 1, 2  # 2 = tensor-core kernel v1 on plain fp32 rows (splits inside the gather loop)
+ROWS_F32, ROWS_SPLIT = 0, 1           # activation layouts: [n, C] fp32 | [n][2][C] tf32 hi/lo halves
 _default_precision = [FP32]
 
 
@@ -63,7 +64,7 @@ class _IndexSet:
 class SparseCooTensor:
     def __init__(self, index, values=None, channels=None, pending=None):
         self.index = index
-        self._values = values
+        self._vals = {ROWS_F32: values, ROWS_SPLIT: None}
         self._pending = pending
         self.channels = channels if channels is not None else values.shape[1]
 
@@ -72,11 +73,29 @@ class SparseCooTensor:
     def shape(self):
         return [self.index.batch] + self.index.spatial + [self.channels]
 
-    def values(self):
+    def get(self, layout):
+        """Row values in the requested layout; launches the pending fused kernel (asking it for this layout) or
+        converts from the other layout with one small kernel."""
+        v = self._vals[layout]
+        if v is not None:
+            return v
         if self._pending is not None:
-            self._values = _run(self._pending)
-            self._pending = None
-        return self._values
+            p, self._pending = self._pending, None
+            _run(p, self, layout)
+            v = self._vals[layout]
+            if v is not None:
+                return v
+        other = 1 - layout
+        src = self._vals[other]
+        dst = torch.empty((self.index.cap, self.channels * (2 if layout == ROWS_SPLIT else 1)), dtype=torch.float32,
+                          device=src.device)
+        check(lib().p3d_rows_convert_layout(ptr(src), other, ptr(self.index.num), self.index.cap, self.channels, ptr(dst),
+                                            stream(src.device)), "rows_convert_layout")
+        self._vals[layout] = dst
+        return dst
+
+    def values(self):
+        return self.get(ROWS_F32)
 
     def indices(self):
         """[4, cap] like paddle (columns beyond nnz() are padding)."""
@@ -118,24 +137,40 @@ class _Pending:
 PROFILE = None  # set to a list to record (cin, cout, K, precision, nbr, num, start_event, end_event) per conv launch
 
 
-def _run(p):
-    xin = p.x.values()
-    dev = xin.device
-    out = torch.empty((p.cap, p.cout), dtype=torch.float32, device=dev)
-    res = p.residual.values() if p.residual is not None else None
+def _run(p, t, want):
+    """Launch the fused gather-GEMM of pending `p` and store its result into tensor `t` (layout `want` when the
+    kernel can produce it directly)."""
+    L = lib()
+    dev = p.nbr.device
+    st = torch.cuda.current_stream(dev)
     if PROFILE is not None:
-        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s.record(torch.cuda.current_stream(dev))
-        check(lib().p3d_sparse_conv_gather_gemm(ptr(xin), ptr(p.nbr), ptr(p.num), p.cap, p.K, p.cin, p.cout,
-                                                ptr(p.weight), ptr(p.scale), ptr(p.shift), ptr(res), int(p.relu),
-                                                int(p.precision), ptr(out), stream(dev)), "sparse_conv_gather_gemm")
-        e.record(torch.cuda.current_stream(dev))
-        PROFILE.append((p.cin, p.cout, p.K, p.precision, p.nbr, p.num, s, e))
-        return out
-    check(lib().p3d_sparse_conv_gather_gemm(ptr(xin), ptr(p.nbr), ptr(p.num), p.cap, p.K, p.cin, p.cout,
+        s_ev, e_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if p.precision == TF32X3:
+        xin = p.x.get(ROWS_SPLIT)
+        res = p.residual.get(ROWS_SPLIT) if p.residual is not None else None
+        out_f32 = torch.empty((p.cap, p.cout), dtype=torch.float32, device=dev) if want == ROWS_F32 else None
+        out_split = torch.empty((p.cap, 2 * p.cout), dtype=torch.float32, device=dev) if want == ROWS_SPLIT else None
+        if PROFILE is not None:
+            s_ev.record(st)
+        check(L.p3d_sparse_conv_gather_gemm_split(ptr(xin), ptr(p.nbr), ptr(p.num), p.cap, p.K, p.cin, p.cout,
+                                                  ptr(p.weight), ptr(p.scale), ptr(p.shift), ptr(res), int(p.relu),
+                                                  ptr(out_f32), ptr(out_split), stream(dev)),
+              "sparse_conv_gather_gemm_split")
+        t._vals[ROWS_F32], t._vals[ROWS_SPLIT] = out_f32, out_split
+    else:
+        xin = p.x.get(ROWS_F32)
+        res = p.residual.get(ROWS_F32) if p.residual is not None else None
+        out = torch.empty((p.cap, p.cout), dtype=torch.float32, device=dev)
+        if PROFILE is not None:
+            s_ev.record(st)
+        check(L.p3d_sparse_conv_gather_gemm(ptr(xin), ptr(p.nbr), ptr(p.num), p.cap, p.K, p.cin, p.cout,
                                             ptr(p.weight), ptr(p.scale), ptr(p.shift), ptr(res), int(p.relu),
-                                            int(p.precision), ptr(out), stream(dev)), "sparse_conv_gather_gemm")
-    return out
+                                            1 if p.precision == TF32X3_F32ROWS else 0, ptr(out), stream(dev)),
+              "sparse_conv_gather_gemm")
+        t._vals[ROWS_F32] = out
+    if PROFILE is not None:
+        e_ev.record(st)
+        PROFILE.append((p.cin, p.cout, p.K, p.precision, p.nbr, p.num, s_ev, e_ev))
 
 
 def _affine_act(x, scale, shift, residual, relu):
@@ -225,7 +260,7 @@ class _ConvBase(_Layer):
         p.x, p.K, p.cin, p.cout = x, K, self.in_channels, self.out_channels
         p.weight, p.scale, p.shift, p.residual, p.relu = self.weight, None, self.bias, None, False
         p.precision = self.precision if self.precision is not None else _default_precision[0]
-        if p.precision == TF32X3:
+        if p.precision in (TF32X3, TF32X3_F32ROWS):
             if not lib().p3d_sparse_conv_packed_weight_bytes(K, self.in_channels, self.out_channels) or K > 32:
                 p.precision = FP32  # e.g. the 5-channel input layer stays on the exact fp32 path
             else:
