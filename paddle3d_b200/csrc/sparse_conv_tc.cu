@@ -241,12 +241,12 @@ __global__ void __launch_bounds__(kThreads, 2) gather_gemm_tf32x3_kernel(const f
         tc_fence_after();
         if (lane == 0) {
           const uint32_t a_hi = smem_u32(a_base + sa * C::A_STAGE), a_lo = a_hi + C::A_TILE;
-          const uint32_t b_hi = smem_u32(b_base + sb * C::B_STAGE), b_lo = b_hi + C::B_TILE;
+          const uint32_t b_hi = smem_u32(b_base + sb * C::B_STAGE), b_lo = b_hi + COUT * 16;  // lo rows follow the hi rows
 #pragma unroll
           for (int j = 0; j < C::KC / 8; ++j) {
-            const uint32_t ao = static_cast<uint32_t>(2 * j) * (kM * 16), bo = static_cast<uint32_t>(2 * j) * (COUT * 16);
+            const uint32_t ao = static_cast<uint32_t>(2 * j) * (kM * 16), bo = static_cast<uint32_t>(2 * j) * (2 * COUT * 16);
             const uint64_t dah = smem_desc(a_hi + ao, kM * 16, 128), dal = smem_desc(a_lo + ao, kM * 16, 128);
-            const uint64_t dbh = smem_desc(b_hi + bo, COUT * 16, 128), dbl = smem_desc(b_lo + bo, COUT * 16, 128);
+            const uint64_t dbh = smem_desc(b_hi + bo, 2 * COUT * 16, 128), dbl = smem_desc(b_lo + bo, 2 * COUT * 16, 128);
             const uint32_t first = (use | j) ? 1u : 0u;
             umma_tf32(tmem_base, dal, dbh, C::IDESC, first);                               // acc 0
             umma_tf32(tmem_base + (C::NACC == 3 ? COUT : 0), dah, dbl, C::IDESC, C::NACC == 3 ? first : 1u);  // acc 1 (or 0)
@@ -285,25 +285,24 @@ __global__ void __launch_bounds__(kThreads, 2) gather_gemm_tf32x3_kernel(const f
   }
 }
 
-// packed[tap][g][hl][c][n][j] = split(W[tap][g*KC + 4c + j][n])
+// packed[tap][g][c][hl * Cout + n][j] = split(W[tap][g*KC + 4c + j][n]): per (tap, 16-channel chunk) a K-major
+// operand of 2*Cout rows (tf32 hi rows, then lo rows), so [B_hi | B_lo] is ONE UMMA operand with N = 2*Cout.
 __global__ void __launch_bounds__(256) pack_weights_kernel(const float *__restrict__ w, int K, int Cin, int Cout,
                                                            float *__restrict__ packed) {
   const long long q = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   const long long total = static_cast<long long>(K) * Cin * Cout;
   if (q >= total) return;
-  const int KC = kc_of(Cin), G = Cin / KC, CH = KC / 4;
+  const int KC = kc_of(Cin), G = Cin / KC;
   const int n = static_cast<int>(q % Cout);
   const int ci = static_cast<int>((q / Cout) % Cin);
   const int t = static_cast<int>(q / (static_cast<long long>(Cout) * Cin));
   const int g = ci / KC, c = (ci % KC) / 4, j = ci & 3;
   float hi, lo;
   split_tf32(w[q], hi, lo);
-  const size_t tile = static_cast<size_t>(KC) * Cout;  // floats in one hi (or lo) slice
-  const size_t base = (static_cast<size_t>(t) * G + g) * 2 * tile;
-  const size_t off = (static_cast<size_t>(c) * Cout + n) * 4 + j;
-  (void)CH;
-  packed[base + off] = hi;
-  packed[base + tile + off] = lo;
+  const size_t stage = static_cast<size_t>(2) * KC * Cout;  // floats per (tap, g)
+  const size_t base = (static_cast<size_t>(t) * G + g) * stage + static_cast<size_t>(c) * (2 * Cout) * 4;
+  packed[base + static_cast<size_t>(n) * 4 + j] = hi;
+  packed[base + static_cast<size_t>(Cout + n) * 4 + j] = lo;
 }
 
 template <int CIN, int COUT>

@@ -23,25 +23,32 @@ using namespace tc;
 
 template <int CIN, int COUT>
 struct Cfg {
-  static constexpr int KC = 16;                   // channels per pipeline use
+  // One pipeline "use" = one tap x KC input channels for the CTA's 128 rows.  Every use costs ~800 cycles of
+  // fixed skeleton time in the single MMA-issuing warp (barrier wait, fences, commit — measured in-kernel with
+  // gathers, weight copies and MMAs all disabled), so uses are made as large as shared memory allows.
+  static constexpr int KC = (CIN >= 64) ? 32 : 16;
   static constexpr int G = CIN / KC;
-  static constexpr int A_TILE = KC * kM * 4;      // 8 KB, one of hi / lo
-  static constexpr int B_TILE = KC * COUT * 4;
+  static constexpr int CH = KC / 4;                      // 16-byte k-chunks per use
+  static constexpr int A_TILE = KC * kM * 4;             // one of hi / lo
   static constexpr int A_STAGE = 2 * A_TILE;
-  static constexpr int B_STAGE = 2 * B_TILE;
-  static constexpr int SA = (COUT <= 64) ? 4 : 3;
-  static constexpr int SB_RAW = (96 * 1024 - SA * A_STAGE) / B_STAGE;
-  static constexpr int SB = SB_RAW > 8 ? 8 : SB_RAW;
-  static constexpr int RING_BYTES = SA * A_STAGE + SB * B_STAGE;
-  // Independent TMEM accumulators: back-to-back tcgen05.mma into ONE accumulator serialise on its dependency
-  // latency (~200 cycles each, measured), so the three 3xTF32 products go to separate column ranges and are summed
-  // in the epilogue.  Cout = 128 keeps two (256 columns) so that two CTAs still fit the 512 TMEM columns of an SM.
-  static constexpr int NACC = (COUT <= 64) ? 3 : 2;
-  static constexpr int TMEM_COLS = (NACC * COUT <= 32) ? 32 : (NACC * COUT <= 64) ? 64 : (NACC * COUT <= 128) ? 128
-                                   : (NACC * COUT <= 256) ? 256 : 512;
+  static constexpr int B_STAGE = 2 * KC * COUT * 4;      // [chunk][hi rows | lo rows][16 B]
+  static constexpr int STAGE = A_STAGE + B_STAGE;        // ONE ring: rows and weights of a use share a slot
+  static constexpr int BUDGET = (COUT <= 32) ? 100 * 1024 : 192 * 1024;   // two CTAs per SM for the narrow layers
+  static constexpr int S_RAW = BUDGET / STAGE;
+  static constexpr int STAGES = S_RAW > 8 ? 8 : (S_RAW < 2 ? 2 : S_RAW);
+  static constexpr int MIN_CTAS = (COUT <= 32) ? 2 : 1;
+  // Two MMAs per 8-wide k-step: [B_hi | B_lo] is one K-major operand of 2*Cout rows, so
+  //   acc[0 .. 2N)   += A_hi x [B_hi | B_lo]      (N' = 2*Cout)
+  //   acc[2N .. 3N)  += A_lo x B_hi               (N  = Cout)
+  // and the epilogue adds the three column ranges (fewer, wider instructions: each tcgen05.mma has a fixed issue
+  // cost that does not depend on its size).
+  static constexpr int TMEM_COLS = (3 * COUT <= 64) ? 64 : (3 * COUT <= 128) ? 128 : (3 * COUT <= 256) ? 256 : 512;
+  static constexpr uint32_t IDESC2 = (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>((2 * COUT) >> 3) << 17) |
+                                     (static_cast<uint32_t>(kM >> 4) << 24);
   static constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(COUT >> 3) << 17) |
                                     (static_cast<uint32_t>(kM >> 4) << 24);
-  static_assert(CIN % 16 == 0 && COUT % 16 == 0 && COUT <= 256, "tensor-core path needs 16-channel multiples");
+  static_assert(CIN % 16 == 0 && COUT % 16 == 0 && COUT <= 128, "tensor-core path needs 16-channel multiples");
+  static_assert(MIN_CTAS * TMEM_COLS <= 512, "TMEM over-subscribed");
 };
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, bool valid) {
@@ -51,45 +58,53 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, bool v
 __device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }
+// Warp-uniform issue: every lane executes the instruction stream (so the descriptors stay in uniform registers
+// instead of going through a per-MMA R2UR waterfall), one elected lane issues.
+__device__ __forceinline__ void umma_tf32_elect(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                                uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p, e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "@e tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_elect(uint32_t bar) {
+  asm volatile(
+      "{\n\t.reg .pred e;\n\t"
+      "elect.sync _|e, 0xffffffff;\n\t"
+      "@e tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar)
+      : "memory");
+}
 
 template <int CIN, int COUT>
-__global__ void __launch_bounds__(kThreads, 2) gather_gemm_split_kernel(const float *__restrict__ in_split,
-                                                                        const int32_t *__restrict__ nbr,
-                                                                        const int32_t *__restrict__ n_out_dev,
-                                                                        long long n_cap, int K,
-                                                                        const float *__restrict__ packed_w,
-                                                                        const float *__restrict__ scale,
-                                                                        const float *__restrict__ shift,
-                                                                        const float *__restrict__ residual_split,
-                                                                        int relu, float *__restrict__ out_f32,
-                                                                        float *__restrict__ out_split,
-                                                                        long long *__restrict__ dbg) {
+__global__ void __launch_bounds__(kThreads, Cfg<CIN, COUT>::MIN_CTAS)
+    gather_gemm_split_kernel(const float *__restrict__ in_split, const int32_t *__restrict__ nbr,
+                             const int32_t *__restrict__ n_out_dev, long long n_cap, int K,
+                             const float *__restrict__ packed_w, const float *__restrict__ scale,
+                             const float *__restrict__ shift, const float *__restrict__ residual_split, int relu,
+                             float *__restrict__ out_f32, float *__restrict__ out_split, long long *__restrict__ dbg) {
   // dbg (optional, CTA 0 only): per-use clock64 timeline, 8 slots per use:
   //   0 producer(warp0): slot free   1 producer: cp.async issued   2 TMA: slot free   3 TMA: issued
-  //   4 MMA: weights landed          5 MMA: rows landed            6 MMA: issued + committed
+  //   5 MMA: slot full               6 MMA: issued + committed
   using C = Cfg<CIN, COUT>;
   const long long n = n_out_dev ? min(static_cast<long long>(n_out_dev[0]), n_cap) : n_cap;
   if (static_cast<long long>(blockIdx.x) * kM >= n) return;
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t *a_base = smem;
-  uint8_t *b_base = smem + C::SA * C::A_STAGE;
-  int32_t *s_nbr = reinterpret_cast<int32_t *>(smem + C::RING_BYTES);  // [kM][K]
-  __shared__ __align__(8) unsigned long long s_bar[4 + 4 + 8 + 8 + 1];
-  constexpr int kAF = 0, kAE = 4, kBF = 8, kBE = 16, kTF = 24;
+  int32_t *s_nbr = reinterpret_cast<int32_t *>(smem + C::STAGES * C::STAGE);  // [kM][K]
+  __shared__ __align__(8) unsigned long long s_bar[8 + 8 + 1];  // full[8] empty[8] tmem_full
+  constexpr int kF = 0, kE = 8, kTF = 16;
   __shared__ uint32_t s_tmem_base;
   __shared__ uint32_t s_active;
 
   const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
   if (tid == kProducers) {
-    for (int s = 0; s < C::SA; ++s) {
-      mbar_init(smem_u32(&s_bar[kAF + s]), kProducers);  // one cp.async-completion arrival per producer thread
-      mbar_init(smem_u32(&s_bar[kAE + s]), 1);
-    }
-    for (int s = 0; s < C::SB; ++s) {
-      mbar_init(smem_u32(&s_bar[kBF + s]), 1);
-      mbar_init(smem_u32(&s_bar[kBE + s]), 1);
+    for (int s = 0; s < C::STAGES; ++s) {
+      mbar_init(smem_u32(&s_bar[kF + s]), kProducers + 1);  // 128 cp.async completions + the weight copy's expect_tx
+      mbar_init(smem_u32(&s_bar[kE + s]), 1);               // tcgen05.commit
     }
     mbar_init(smem_u32(&s_bar[kTF]), 1);
     fence_mbar_init();
@@ -105,6 +120,7 @@ __global__ void __launch_bounds__(kThreads, 2) gather_gemm_split_kernel(const fl
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = s_tmem_base;
+  const uint32_t ring = smem_u32(smem);
 
   int use_base = 0;  // pipeline uses consumed by earlier tiles of this CTA (ring phases keep running)
   int tile_it = 0;
@@ -129,6 +145,9 @@ __global__ void __launch_bounds__(kThreads, 2) gather_gemm_split_kernel(const fl
 
     if (wid < 4) {
       // ---------------------------------------------------------------- producers (cp.async gathers)
+      // a warp instruction covers 8 rows x 4 k-chunks: 64 contiguous bytes per gathered row, 512 contiguous bytes of
+      // shared memory (A tile: k-chunk stride LBO = 128 B inside a 4-chunk block, 8-row groups SBO = 512 B apart,
+      // 16-channel blocks 8 KB apart).
       const int sub = lane >> 2, ch = lane & 3;
       int use = use_base;
       for (int t = 0; t < K; ++t) {
@@ -137,19 +156,22 @@ __global__ void __launch_bounds__(kThreads, 2) gather_gemm_split_kernel(const fl
 #pragma unroll
         for (int q = 0; q < 4; ++q) src[q] = s_nbr[(wid * 32 + q * 8 + sub) * K + t];
         for (int g = 0; g < C::G; ++g, ++use) {
-          const int s = use % C::SA;
-          mbar_wait(smem_u32(&s_bar[kAE + s]), (static_cast<uint32_t>(use / C::SA) & 1u) ^ 1u);
+          const int s = use % C::STAGES;
+          mbar_wait(smem_u32(&s_bar[kE + s]), (static_cast<uint32_t>(use / C::STAGES) & 1u) ^ 1u);
           if (dbg && blockIdx.x == 0 && tid == 0 && use < 512) dbg[use * 8 + 0] = clock64();
-          const uint32_t st = smem_u32(a_base + s * C::A_STAGE);
+          const uint32_t st = ring + static_cast<uint32_t>(s * C::STAGE);
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const bool ok = src[q] >= 0;
             const float *p = in_split + (ok ? static_cast<size_t>(src[q]) * (2 * CIN) : 0) + g * C::KC + ch * 4;
             const uint32_t d = st + static_cast<uint32_t>((wid * 4 + q) * 512 + ch * 128 + sub * 16);
-            cp_async16(d, p, ok);                         // hi
-            cp_async16(d + C::A_TILE, p + CIN, ok);       // lo
+#pragma unroll
+            for (int b = 0; b < C::KC / 16; ++b) {  // 16-channel blocks of this use
+              cp_async16(d + b * (kM * 64), p + b * 16, ok);                    // hi
+              cp_async16(d + b * (kM * 64) + C::A_TILE, p + b * 16 + CIN, ok);  // lo
+            }
           }
-          cp_async_arrive_noinc(smem_u32(&s_bar[kAF + s]));
+          cp_async_arrive_noinc(smem_u32(&s_bar[kF + s]));
           if (dbg && blockIdx.x == 0 && tid == 0 && use < 512) dbg[use * 8 + 1] = clock64();
         }
       }
@@ -171,7 +193,7 @@ __global__ void __launch_bounds__(kThreads, 2) gather_gemm_split_kernel(const fl
                 "=r"(a[8]), "=r"(a[9]), "=r"(a[10]), "=r"(a[11]), "=r"(a[12]), "=r"(a[13]), "=r"(a[14]), "=r"(a[15])
               : "r"(taddr + static_cast<uint32_t>(c0)));
 #pragma unroll
-          for (int acc = 1; acc < C::NACC; ++acc) {
+          for (int acc = 1; acc < 3; ++acc) {
             uint32_t b[16];
             asm volatile(
                 "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, "
@@ -183,7 +205,6 @@ __global__ void __launch_bounds__(kThreads, 2) gather_gemm_split_kernel(const fl
 #pragma unroll
             for (int j = 0; j < 16; ++j) a[j] = __float_as_uint(__uint_as_float(a[j]) + __uint_as_float(b[j]));
           }
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
         } else {
 #pragma unroll
           for (int j = 0; j < 16; ++j) a[j] = 0u;
@@ -231,54 +252,50 @@ __global__ void __launch_bounds__(kThreads, 2) gather_gemm_split_kernel(const fl
       }
       tc_fence_before();
     } else if (wid == 4) {
-      // ---------------------------------------------------------------- MMA issuer
+      // ---------------------------------------------------------------- MMA issuer (whole warp runs the stream)
       if (n_uses == 0) {
         if (lane == 0) mbar_arrive(smem_u32(&s_bar[kTF]));
       } else {
         for (int u = 0; u < n_uses; ++u) {
           const int use = use_base + u;
-          const int sa = use % C::SA, sb = use % C::SB;
-          mbar_wait(smem_u32(&s_bar[kBF + sb]), static_cast<uint32_t>(use / C::SB) & 1u);
-          if (dbg && blockIdx.x == 0 && lane == 0 && use < 512) dbg[use * 8 + 4] = clock64();
-          mbar_wait(smem_u32(&s_bar[kAF + sa]), static_cast<uint32_t>(use / C::SA) & 1u);
+          const int s = use % C::STAGES;
+          mbar_wait(smem_u32(&s_bar[kF + s]), static_cast<uint32_t>(use / C::STAGES) & 1u);
           if (dbg && blockIdx.x == 0 && lane == 0 && use < 512) dbg[use * 8 + 5] = clock64();
           fence_proxy_async();  // cp.async (generic proxy) writes -> tensor-core (async proxy) reads
           tc_fence_after();
-          if (lane == 0) {
-            const uint32_t a_hi = smem_u32(a_base + sa * C::A_STAGE), a_lo = a_hi + C::A_TILE;
-            const uint32_t b_hi = smem_u32(b_base + sb * C::B_STAGE), b_lo = b_hi + C::B_TILE;
+          const uint32_t a_hi = ring + static_cast<uint32_t>(s * C::STAGE), a_lo = a_hi + C::A_TILE;
+          const uint32_t b_all = a_hi + C::A_STAGE;
 #pragma unroll
-            for (int j = 0; j < C::KC / 8; ++j) {
-              const uint32_t ao = static_cast<uint32_t>(2 * j) * 128, bo = static_cast<uint32_t>(2 * j) * (COUT * 16);
-              const uint64_t dah = smem_desc(a_hi + ao, 128, 512), dal = smem_desc(a_lo + ao, 128, 512);
-              const uint64_t dbh = smem_desc(b_hi + bo, COUT * 16, 128), dbl = smem_desc(b_lo + bo, COUT * 16, 128);
-              const uint32_t first = (u | j) ? 1u : 0u;
-              umma_tf32(tmem_base, dal, dbh, C::IDESC, first);                               // acc 0
-              umma_tf32(tmem_base + (C::NACC == 3 ? COUT : 0), dah, dbl, C::IDESC, C::NACC == 3 ? first : 1u);
-              umma_tf32(tmem_base + (C::NACC - 1) * COUT, dah, dbh, C::IDESC, first);         // last acc
-            }
-            umma_commit(smem_u32(&s_bar[kAE + sa]));
-            umma_commit(smem_u32(&s_bar[kBE + sb]));
-            if (u == n_uses - 1) umma_commit(smem_u32(&s_bar[kTF]));
-            if (dbg && blockIdx.x == 0 && use < 512) dbg[use * 8 + 6] = clock64();
+          for (int j = 0; j < C::KC / 8; ++j) {
+            // k-step j: 16-channel block j / 2, chunk pair (j & 1) inside it
+            const uint32_t ao = static_cast<uint32_t>(j >> 1) * (kM * 64) + static_cast<uint32_t>(j & 1) * 256;
+            const uint32_t bo = static_cast<uint32_t>(2 * j) * (2 * COUT * 16);
+            const uint64_t dah = smem_desc(a_hi + ao, 128, 512), dal = smem_desc(a_lo + ao, 128, 512);
+            const uint64_t db = smem_desc(b_all + bo, 2 * COUT * 16, 128);  // rows 0..N-1 = hi, N..2N-1 = lo
+            const uint32_t first = (u | j) ? 1u : 0u;
+            umma_tf32_elect(tmem_base, dah, db, C::IDESC2, first);             // A_hi x [B_hi | B_lo]
+            umma_tf32_elect(tmem_base + 2 * COUT, dal, db, C::IDESC, first);   // A_lo x B_hi
           }
-          __syncwarp();
+          umma_commit_elect(smem_u32(&s_bar[kE + s]));
+          if (u == n_uses - 1) umma_commit_elect(smem_u32(&s_bar[kTF]));
+          if (dbg && blockIdx.x == 0 && lane == 0 && use < 512) dbg[use * 8 + 6] = clock64();
         }
       }
       tc_fence_before();
     } else {
-      // ---------------------------------------------------------------- weight TMA
+      // ---------------------------------------------------------------- weight TMA (one lane)
       if (lane == 0) {
         int use = use_base;
         for (int t = 0; t < K; ++t) {
           if (!((active >> t) & 1u)) continue;
           for (int g = 0; g < C::G; ++g, ++use) {
-            const int sb = use % C::SB;
-            mbar_wait(smem_u32(&s_bar[kBE + sb]), (static_cast<uint32_t>(use / C::SB) & 1u) ^ 1u);
+            const int s = use % C::STAGES;
+            mbar_wait(smem_u32(&s_bar[kE + s]), (static_cast<uint32_t>(use / C::STAGES) & 1u) ^ 1u);
             if (dbg && blockIdx.x == 0 && use < 512) dbg[use * 8 + 2] = clock64();
-            mbar_arrive_expect_tx(smem_u32(&s_bar[kBF + sb]), static_cast<uint32_t>(C::B_STAGE));
-            bulk_g2s(smem_u32(b_base + sb * C::B_STAGE), packed_w + (static_cast<size_t>(t) * C::G + g) * (2 * C::KC * COUT),
-                     static_cast<uint32_t>(C::B_STAGE), smem_u32(&s_bar[kBF + sb]));
+            mbar_arrive_expect_tx(smem_u32(&s_bar[kF + s]), static_cast<uint32_t>(C::B_STAGE));
+            bulk_g2s(ring + static_cast<uint32_t>(s * C::STAGE + C::A_STAGE),
+                     packed_w + (static_cast<size_t>(t) * CIN + g * C::KC) * (2 * COUT), static_cast<uint32_t>(C::B_STAGE),
+                     smem_u32(&s_bar[kF + s]));
             if (dbg && blockIdx.x == 0 && use < 512) dbg[use * 8 + 3] = clock64();
           }
         }
@@ -301,12 +318,13 @@ int launch(const float *in_split, const int32_t *nbr, const int32_t *n_out_dev, 
            const float *packed, const float *scale, const float *shift, const float *residual_split, int relu,
            float *out_f32, float *out_split, cudaStream_t st, long long *dbg = nullptr) {
   using C = Cfg<CIN, COUT>;
-  const size_t smem = static_cast<size_t>(C::RING_BYTES) + static_cast<size_t>(kM) * K * sizeof(int32_t) + 1024;
+  const size_t smem = static_cast<size_t>(C::STAGES) * C::STAGE + static_cast<size_t>(kM) * K * sizeof(int32_t) + 1024;
   if (smem > 227 * 1024) return P3D_ERR_UNSUPPORTED;
   auto kern = gather_gemm_split_kernel<CIN, COUT>;
   P3D_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   const long long tiles = (n_cap + kM - 1) / kM;
-  const unsigned int grid = static_cast<unsigned int>(tiles < 2 * kNumSMs ? tiles : 2 * kNumSMs);
+  const long long slots = static_cast<long long>(kNumSMs) * C::MIN_CTAS;
+  const unsigned int grid = static_cast<unsigned int>(tiles < slots ? tiles : slots);
   kern<<<grid, kThreads, smem, st>>>(in_split, nbr, n_out_dev, n_cap, K, packed, scale, shift, residual_split, relu,
                                      out_f32, out_split, dbg);
   P3D_LAUNCH_CHECK();

@@ -24,7 +24,11 @@ from .._lib import check, host_ints, lib
 from .._mem import ptr, require_cuda, stream, workspace
 from . import pillar_scatter as _ps
 
-FP32, TF32X3, TF32X3_F32ROWS = 0, 1, 2  # 2 = tensor-core kernel v1 on plain fp32 rows (splits inside the gather loop)
+# FP32         exact fp32 FMA on CUDA cores
+# TF32X3       tcgen05 3xTF32 on plain fp32 rows: the tf32 hi/lo split happens inside the gather loop (fastest today)
+# TF32X3_SPLIT tcgen05 3xTF32 on split-layout rows [n][2][C]: cp.async gathers, persistent tiles, split done once in
+#              the producing layer's epilogue (experimental: measured slower than TF32X3)
+FP32, TF32X3, TF32X3_SPLIT = 0, 1, 2
 ROWS_F32, ROWS_SPLIT = 0, 1           # activation layouts: [n, C] fp32 | [n][2][C] tf32 hi/lo halves
 _default_precision = [FP32]
 
@@ -145,7 +149,7 @@ def _run(p, t, want):
     st = torch.cuda.current_stream(dev)
     if PROFILE is not None:
         s_ev, e_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    if p.precision == TF32X3:
+    if p.precision == TF32X3_SPLIT:
         xin = p.x.get(ROWS_SPLIT)
         res = p.residual.get(ROWS_SPLIT) if p.residual is not None else None
         out_f32 = torch.empty((p.cap, p.cout), dtype=torch.float32, device=dev) if want == ROWS_F32 else None
@@ -165,7 +169,7 @@ def _run(p, t, want):
             s_ev.record(st)
         check(L.p3d_sparse_conv_gather_gemm(ptr(xin), ptr(p.nbr), ptr(p.num), p.cap, p.K, p.cin, p.cout,
                                             ptr(p.weight), ptr(p.scale), ptr(p.shift), ptr(res), int(p.relu),
-                                            1 if p.precision == TF32X3_F32ROWS else 0, ptr(out), stream(dev)),
+                                            1 if p.precision == TF32X3 else 0, ptr(out), stream(dev)),
               "sparse_conv_gather_gemm")
         t._vals[ROWS_F32] = out
     if PROFILE is not None:
@@ -260,7 +264,7 @@ class _ConvBase(_Layer):
         p.x, p.K, p.cin, p.cout = x, K, self.in_channels, self.out_channels
         p.weight, p.scale, p.shift, p.residual, p.relu = self.weight, None, self.bias, None, False
         p.precision = self.precision if self.precision is not None else _default_precision[0]
-        if p.precision in (TF32X3, TF32X3_F32ROWS):
+        if p.precision in (TF32X3, TF32X3_SPLIT):
             if not lib().p3d_sparse_conv_packed_weight_bytes(K, self.in_channels, self.out_channels) or K > 32:
                 p.precision = FP32  # e.g. the 5-channel input layer stays on the exact fp32 path
             else:
