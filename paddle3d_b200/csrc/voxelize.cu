@@ -234,46 +234,60 @@ __global__ void __launch_bounds__(256) vox_slots_kernel(const int32_t *__restric
 // ---------------------------------------------------------------- K4
 __device__ __forceinline__ void st_stream(float4 *p, float4 v) { __stcs(p, v); }
 
+constexpr int kWriteUnroll = 4;  // float4 stores per thread: 4 independent lists -> points -> store chains in flight
+
 __global__ void __launch_bounds__(256) vox_write_kernel(const float *__restrict__ points, int F, int P, int V,
                                                         const int32_t *__restrict__ lists,
                                                         const int32_t *__restrict__ num_voxels_dev,
                                                         float *__restrict__ voxels, int32_t *__restrict__ coords,
                                                         int32_t *__restrict__ npv, long long total4,
                                                         long long total) {
-  const long long q = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (q < total4) {
-    const long long e0 = q * 4;
-    const int PF = P * F;
-    int v = static_cast<int>(e0 / PF);
-    int r = static_cast<int>(e0 - static_cast<long long>(v) * PF);
-    int s = r / F;
-    int f = r - s * F;
-    int idx = lists[static_cast<size_t>(v) * P + s];
-    float o[4];
+  const int PF = P * F;
+  const long long blk0 = static_cast<long long>(blockIdx.x) * (256 * kWriteUnroll);
+  float4 o[kWriteUnroll];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      o[k] = (idx != kInf) ? __ldg(points + static_cast<size_t>(idx) * F + f) : 0.f;
-      if (++f == F) {
-        f = 0;
-        if (++s == P) {
-          s = 0;
-          ++v;
+  for (int u = 0; u < kWriteUnroll; ++u) {
+    const long long q = blk0 + u * 256 + threadIdx.x;  // consecutive threads -> consecutive float4: coalesced
+    float r[4] = {0.f, 0.f, 0.f, 0.f};
+    if (q < total4) {
+      const long long e0 = q * 4;
+      int v = static_cast<int>(e0 / PF);
+      int rem = static_cast<int>(e0 - static_cast<long long>(v) * PF);
+      int s = rem / F;
+      int f = rem - s * F;
+      int idx = __ldg(lists + static_cast<size_t>(v) * P + s);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        r[k] = (idx != kInf) ? __ldg(points + static_cast<size_t>(idx) * F + f) : 0.f;
+        if (++f == F) {
+          f = 0;
+          if (++s == P) {
+            s = 0;
+            ++v;
+          }
+          if (k < 3 && v < V) idx = __ldg(lists + static_cast<size_t>(v) * P + s);
         }
-        if (k < 3 && v < V) idx = lists[static_cast<size_t>(v) * P + s];
       }
     }
-    st_stream(reinterpret_cast<float4 *>(voxels) + q, make_float4(o[0], o[1], o[2], o[3]));
-  } else if (q == total4) {
+    o[u] = make_float4(r[0], r[1], r[2], r[3]);
+  }
+#pragma unroll
+  for (int u = 0; u < kWriteUnroll; ++u) {
+    const long long q = blk0 + u * 256 + threadIdx.x;
+    if (q < total4) st_stream(reinterpret_cast<float4 *>(voxels) + q, o[u]);
+  }
+  const long long gtid = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
+  if (gtid == 0) {
     // scalar tail when V*P*F is not a multiple of 4
     for (long long e = total4 * 4; e < total; ++e) {
-      const int v = static_cast<int>(e / (P * F));
-      const int r = static_cast<int>(e - static_cast<long long>(v) * P * F);
-      const int idx = lists[static_cast<size_t>(v) * P + r / F];
-      voxels[e] = (idx != kInf) ? points[static_cast<size_t>(idx) * F + r % F] : 0.f;
+      const int v = static_cast<int>(e / PF);
+      const int rem = static_cast<int>(e - static_cast<long long>(v) * PF);
+      const int idx = lists[static_cast<size_t>(v) * P + rem / F];
+      voxels[e] = (idx != kInf) ? points[static_cast<size_t>(idx) * F + rem % F] : 0.f;
     }
   }
-  if (q < V) {
-    const int v = static_cast<int>(q);
+  // per-voxel outputs: one thread per voxel, strided over the grid
+  for (long long v = gtid; v < V; v += static_cast<long long>(gridDim.x) * 256) {
     int cnt = 0;
     for (int s = 0; s < P; ++s) cnt += (lists[static_cast<size_t>(v) * P + s] != kInf);
     npv[v] = cnt;
@@ -400,9 +414,10 @@ extern "C" int p3d_hard_voxelize(const float *points, int64_t num_points, int nu
   if (rc) return rc;
   const long long total = static_cast<long long>(max_voxels) * max_points * num_point_dim;
   const long long total4 = total / 4;
-  long long threads = total4 + 1;
-  if (threads < max_voxels) threads = max_voxels;
-  vox_write_kernel<<<div_up(threads, 256), 256, 0, st>>>(points, num_point_dim, max_points, max_voxels, w.lists,
+  const long long per_block = 256 * kWriteUnroll;
+  long long blocks = (total4 + per_block - 1) / per_block;
+  if (blocks < 1) blocks = 1;
+  vox_write_kernel<<<static_cast<unsigned int>(blocks), 256, 0, st>>>(points, num_point_dim, max_points, max_voxels, w.lists,
                                                         num_voxels, voxels, coords, num_points_per_voxel, total4,
                                                         total);
   P3D_LAUNCH_CHECK();

@@ -1,0 +1,124 @@
+#!/usr/bin/env python
+"""Op-level roofline table for the HBM-bound ops of the hot path at their BASELINE.json configurations
+(SURVEY.md §8d byte counts).  Each op call is captured into a CUDA graph and every replay is timed on its own with CUDA events on the
+launching stream after an L2 flush (a 256 MB write), so neither cached inputs nor host launch gaps distort it.  Output: one JSON line per op.
+
+    python tools/op_bench.py [--iters 30] [--only voxelize,scatter,bev_pool,nms,postprocess]
+Run it under ncu for the committed captures (profiles/), e.g.
+    ncu --set full --clock-control none -k regex:'vox_write|scat_write|bev_fwd' -c 6 -o gpurun_out/ops python tools/op_bench.py --iters 2
+"""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+
+from paddle3d_b200 import synth  # noqa: E402
+from paddle3d_b200.ops import bev_pool_v2, centerpoint_postprocess, iou3d_nms, pillar_scatter, voxelize  # noqa: E402
+
+
+def timed(fn, iters, flush):
+    """Device time of one call of `fn`: the call is captured into a CUDA graph (its launches then run back to back,
+    without Python / ctypes gaps between them) and each replay is bracketed by events after an L2 flush."""
+    st = torch.cuda.Stream()
+    ts = []
+    with torch.cuda.stream(st):
+        for _ in range(3):
+            fn()
+        st.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=st):
+            fn()
+        for _ in range(iters):
+            flush.zero_()
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record(st)
+            g.replay()
+            e.record(st)
+            e.synchronize()
+            ts.append(s.elapsed_time(e) * 1e3)
+    ts.sort()
+    return ts[0], ts[len(ts) // 2]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--iters", type=int, default=30)
+    ap.add_argument("--only", default="")
+    args = ap.parse_args()
+    only = set(x for x in args.only.split(",") if x)
+    dev = torch.device("cuda:0")
+    flush = torch.empty(256 * 2 ** 20, dtype=torch.uint8, device=dev)
+    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peak = json.load(open(pk))["hbm_gbs"] if os.path.exists(pk) else 6650.0
+    out = []
+
+    def report(name, cfg, nbytes, fn, note=""):
+        if only and name.split(":")[0] not in only:
+            return
+        mn, med = timed(fn, args.iters, flush)
+        line = {"op": name, "config": cfg, "algorithmic_bytes": nbytes, "us_min": round(mn, 2), "us_median": round(med, 2),
+                "achieved_gbs": round(nbytes / (med * 1e-6) / 1e9, 1), "peak_gbs": peak,
+                "frac": round(nbytes / (med * 1e-6) / 1e9 / peak, 4), "note": note}
+        out.append(line)
+        print(json.dumps(line), flush=True)
+
+    # hard_voxelize (whole op, 5 launches) — C2 and C3
+    for cfg, gen in ((synth.C2, synth.lidar_cloud), (synth.C3, synth.lidar_cloud)):
+        pts = torch.from_numpy(gen(cfg, 0)).to(dev)
+        N, F, P, V = pts.shape[0], pts.shape[1], cfg["max_points"], cfg["max_voxels"]
+        nbytes = 4 * N * F + 4 * V * P * F + 12 * V + 4 * V + 4
+        report("voxelize:hard_voxelize", cfg["name"], nbytes,
+               lambda: voxelize.hard_voxelize(pts, cfg["voxel_size"], cfg["point_cloud_range"], P, V),
+               "whole op: vox_init+insert+rank+slots+write")
+        report("voxelize:voxelize_mean", cfg["name"], 4 * N * F + 4 * V * F + 16 * V + 4 * V,
+               lambda: voxelize.voxelize_mean(pts, cfg["voxel_size"], cfg["point_cloud_range"], P, V),
+               "fused VoxelMean front end (no padded tensor)")
+    # PillarScatter — C2: [nv, 64] -> [1, 64, 496, 432]
+    cfg = synth.C2
+    import oracle
+    v, c, n, nv = oracle.hard_voxelize(synth.uniform_cloud(cfg, 1), cfg["voxel_size"], cfg["point_cloud_range"], 4, 40000)
+    k = int(nv[0])
+    coors = torch.from_numpy(np.concatenate([np.zeros((k, 1), np.int32), c[:k]], 1)).to(dev)
+    feats = torch.randn((k, 64), device=dev)
+    report("scatter:pillar_scatter", "C2 nv=%d C=64 496x432" % k, 4 * k * 64 + 16 * k + 4 * 64 * 496 * 432,
+           lambda: pillar_scatter.pillar_scatter(feats, coors, 1, 496, 432), "memset map + scat_map + scat_write")
+    # to_dense_bev — C3 shape [n,128] -> [1,256,180,180]
+    rng = np.random.default_rng(0)
+    occ = np.argwhere(rng.random((1, 2, 180, 180)) < 0.09).astype(np.int32)
+    f2 = torch.randn((len(occ), 128), device=dev)
+    occ_dev = torch.from_numpy(occ).to(dev)
+    report("scatter:sparse_to_dense_bev", "C3 n=%d C=128 2x180x180" % len(occ), 4 * len(occ) * 128 + 16 * len(occ) + 4 * 256 * 180 * 180,
+           lambda: pillar_scatter.sparse_to_dense_bev(f2, occ_dev, 1, (2, 180, 180)))
+    # bev_pool_v2 — C4 reference grid (128x128) and BASELINE grid (200x200)
+    for grid, b in (((128, 128, 1), (-51.2, 51.2)), ((200, 200, 1), (-50.0, 50.0))):
+        d = synth.bev_pool_inputs(5, grid=grid, bounds=(b, b, (-5.0, 3.0)))
+        keys = ["depth", "feat", "ranks_depth", "ranks_feat", "ranks_bev", "interval_lengths", "interval_starts"]
+        t = [torch.from_numpy(d[kk]).to(dev) for kk in keys]
+        npts, nint = len(d["ranks_bev"]), len(d["interval_starts"])
+        nbytes = 12 * npts + 4 * npts + 4 * d["feat"].size + 8 * nint + 4 * int(np.prod(d["bev_feat_shape"]))
+        report("bev_pool:bev_pool_v2", "C4 grid %dx%d n_pts=%d n_int=%d C=80" % (grid[0], grid[1], npts, nint), nbytes,
+               lambda: bev_pool_v2.bev_pool_v2(*t, d["bev_feat_shape"]), "memset + bev_fwd")
+    # NMS — 1000 boxes (latency/ALU bound: report pairs/s instead of an HBM fraction)
+    boxes = torch.from_numpy(synth.random_boxes(1000, 3)).to(dev)
+    report("nms:nms_gpu", "1000 boxes thr 0.2", 28 * 1000 + 8 * 1000 * 16,
+           lambda: iou3d_nms.nms_gpu(boxes, 0.2, device_outputs=True), "ALU/latency bound; bytes = boxes + bit-matrix")
+    # centerpoint_postprocess — 6 tasks 180x180
+    h = synth.centerpoint_head_outputs(0)
+    th = {kk: [torch.from_numpy(x).to(dev) for x in vv] for kk, vv in h.items()}
+    tc = synth.CENTERPOINT_TEST_CFG
+    nb = 4 * sum(x.size for vv in h.values() for x in vv)
+    report("postprocess:centerpoint_postprocess", "6 tasks 180x180", nb,
+           lambda: centerpoint_postprocess.centerpoint_postprocess_device(
+               th["hm"], th["reg"], th["height"], th["dim"], th["vel"], th["rot"], [0.075, 0.075],
+               synth.C3["point_cloud_range"], tc["post_center_limit_range"], synth.label_offsets(), tc["down_ratio"],
+               tc["score_threshold"], tc["nms_iou_threshold"], tc["nms_pre_max_size"], tc["nms_post_max_size"], True),
+           "5 launches, zero host syncs; latency bound")
+
+
+if __name__ == "__main__":
+    main()
