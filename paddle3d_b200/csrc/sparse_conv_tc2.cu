@@ -51,6 +51,10 @@ struct Cfg {
   static_assert(MIN_CTAS * TMEM_COLS <= 512, "TMEM over-subscribed");
 };
 
+// debug only (p3d_debug_set_flags): 1 skip weight copies, 2 skip row gathers, 4 skip MMAs, 8 skip fence.proxy.async,
+// 16 plain mbarrier arrive instead of tcgen05.commit, 32 plain arrive instead of cp.async.mbarrier.arrive.noinc
+__device__ int g_dbg_flags = 0;
+
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, bool valid) {
   const uint32_t sz = valid ? 16u : 0u;  // src-size 0 => 16 bytes of zeros
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(sz) : "memory");
@@ -142,6 +146,7 @@ __global__ void __launch_bounds__(kThreads, Cfg<CIN, COUT>::MIN_CTAS)
     __syncthreads();
     const uint32_t active = s_active;
     const int n_uses = __popc(active) * C::G;
+    const int flags = dbg ? g_dbg_flags : 0;  // only the debug entry point passes dbg
 
     if (wid < 4) {
       // ---------------------------------------------------------------- producers (cp.async gathers)
@@ -167,11 +172,15 @@ __global__ void __launch_bounds__(kThreads, Cfg<CIN, COUT>::MIN_CTAS)
             const uint32_t d = st + static_cast<uint32_t>((wid * 4 + q) * 512 + ch * 128 + sub * 16);
 #pragma unroll
             for (int b = 0; b < C::KC / 16; ++b) {  // 16-channel blocks of this use
+              if (flags & 2) continue;
               cp_async16(d + b * (kM * 64), p + b * 16, ok);                    // hi
               cp_async16(d + b * (kM * 64) + C::A_TILE, p + b * 16 + CIN, ok);  // lo
             }
           }
-          cp_async_arrive_noinc(smem_u32(&s_bar[kF + s]));
+          if (flags & 32)
+            mbar_arrive(smem_u32(&s_bar[kF + s]));
+          else
+            cp_async_arrive_noinc(smem_u32(&s_bar[kF + s]));
           if (dbg && blockIdx.x == 0 && tid == 0 && use < 512) dbg[use * 8 + 1] = clock64();
         }
       }
@@ -261,7 +270,7 @@ __global__ void __launch_bounds__(kThreads, Cfg<CIN, COUT>::MIN_CTAS)
           const int s = use % C::STAGES;
           mbar_wait(smem_u32(&s_bar[kF + s]), static_cast<uint32_t>(use / C::STAGES) & 1u);
           if (dbg && blockIdx.x == 0 && lane == 0 && use < 512) dbg[use * 8 + 5] = clock64();
-          fence_proxy_async();  // cp.async (generic proxy) writes -> tensor-core (async proxy) reads
+          if (!(flags & 8)) fence_proxy_async();  // cp.async (generic proxy) writes -> tensor-core (async proxy) reads
           tc_fence_after();
           const uint32_t a_hi = ring + static_cast<uint32_t>(s * C::STAGE), a_lo = a_hi + C::A_TILE;
           const uint32_t b_all = a_hi + C::A_STAGE;
@@ -273,11 +282,20 @@ __global__ void __launch_bounds__(kThreads, Cfg<CIN, COUT>::MIN_CTAS)
             const uint64_t dah = smem_desc(a_hi + ao, 128, 512), dal = smem_desc(a_lo + ao, 128, 512);
             const uint64_t db = smem_desc(b_all + bo, 2 * COUT * 16, 128);  // rows 0..N-1 = hi, N..2N-1 = lo
             const uint32_t first = (u | j) ? 1u : 0u;
+            if (flags & 4) continue;
             umma_tf32_elect(tmem_base, dah, db, C::IDESC2, first);             // A_hi x [B_hi | B_lo]
             umma_tf32_elect(tmem_base + 2 * COUT, dal, db, C::IDESC, first);   // A_lo x B_hi
           }
-          umma_commit_elect(smem_u32(&s_bar[kE + s]));
-          if (u == n_uses - 1) umma_commit_elect(smem_u32(&s_bar[kTF]));
+          if (flags & 16) {
+            if (lane == 0) {
+              mbar_arrive(smem_u32(&s_bar[kE + s]));
+              if (u == n_uses - 1) mbar_arrive(smem_u32(&s_bar[kTF]));
+            }
+            __syncwarp();
+          } else {
+            umma_commit_elect(smem_u32(&s_bar[kE + s]));
+            if (u == n_uses - 1) umma_commit_elect(smem_u32(&s_bar[kTF]));
+          }
           if (dbg && blockIdx.x == 0 && lane == 0 && use < 512) dbg[use * 8 + 6] = clock64();
         }
       }
@@ -292,10 +310,14 @@ __global__ void __launch_bounds__(kThreads, Cfg<CIN, COUT>::MIN_CTAS)
             const int s = use % C::STAGES;
             mbar_wait(smem_u32(&s_bar[kE + s]), (static_cast<uint32_t>(use / C::STAGES) & 1u) ^ 1u);
             if (dbg && blockIdx.x == 0 && use < 512) dbg[use * 8 + 2] = clock64();
-            mbar_arrive_expect_tx(smem_u32(&s_bar[kF + s]), static_cast<uint32_t>(C::B_STAGE));
-            bulk_g2s(ring + static_cast<uint32_t>(s * C::STAGE + C::A_STAGE),
-                     packed_w + (static_cast<size_t>(t) * CIN + g * C::KC) * (2 * COUT), static_cast<uint32_t>(C::B_STAGE),
-                     smem_u32(&s_bar[kF + s]));
+            if (flags & 1) {
+              mbar_arrive(smem_u32(&s_bar[kF + s]));
+            } else {
+              mbar_arrive_expect_tx(smem_u32(&s_bar[kF + s]), static_cast<uint32_t>(C::B_STAGE));
+              bulk_g2s(ring + static_cast<uint32_t>(s * C::STAGE + C::A_STAGE),
+                       packed_w + (static_cast<size_t>(t) * CIN + g * C::KC) * (2 * COUT), static_cast<uint32_t>(C::B_STAGE),
+                       smem_u32(&s_bar[kF + s]));
+            }
             if (dbg && blockIdx.x == 0 && use < 512) dbg[use * 8 + 3] = clock64();
           }
         }
@@ -406,4 +428,8 @@ extern "C" int p3d_debug_split_timeline_64(const float *in_split, const int32_t 
                                            long long *dbg, p3d_stream_t stream) {
   return tc2::launch<64, 64>(in_split, nbr, n_out_dev, n_out_cap, K, packed_weight, nullptr, nullptr, nullptr, 0, out_f32,
                              nullptr, static_cast<cudaStream_t>(stream), dbg);
+}
+
+extern "C" int p3d_debug_set_flags(int flags) {
+  return cudaMemcpyToSymbol(tc2::g_dbg_flags, &flags, sizeof(int)) == cudaSuccess ? 0 : -3;
 }
