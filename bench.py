@@ -131,15 +131,21 @@ def run_reference(args):
     head = synth.centerpoint_head_outputs(0)
     cf = CpuFrame(cfg, weights, head, synth.CENTERPOINT_TEST_CFG, synth.label_offsets())
     frames = frame_pool(cfg, 4, base=2)
+    t_w = time.perf_counter()
     for i in range(args.warmup):
         cf.run(frames[i % len(frames)])
+    per_frame = (time.perf_counter() - t_w) / max(args.warmup, 1)
+    # bound the run: a full frame costs seconds on the host, so the number of timed frames is capped at what fits
+    # in about three minutes (the per-frame throughput is what is reported, not a total)
+    steps = max(1, min(args.steps, int(180.0 / max(per_frame, 1e-3))))
     t0 = time.perf_counter()
     stages = {}
-    for i in range(args.steps):
+    for i in range(steps):
         r = cf.run(frames[i % len(frames)])
         for k, v in r["times"].items():
             stages[k] = stages.get(k, 0.0) + v
     dt = time.perf_counter() - t0
+    requested, args.steps = args.steps, steps
     fps = args.steps / dt
     cores = oracle.num_threads()
     kind = "port"
@@ -151,7 +157,8 @@ def run_reference(args):
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD},
             "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "stage_ms": {k: 1e3 * v / args.steps for k, v in stages.items()}, "gpu_launches": 0}
+            "stage_ms": {k: 1e3 * v / args.steps for k, v in stages.items()}, "gpu_launches": 0,
+            "steps_requested": requested}
     print(json.dumps(line))
 
 
