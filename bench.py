@@ -210,7 +210,8 @@ def main():
 
     cfg = synth.C3
     precision = {"tf32x3": sp.TF32X3, "tf32x3_split": sp.TF32X3_SPLIT, "fp32": sp.FP32}[args.precision]
-    pipe = CenterPointHotPath(cfg, dev, precision=precision, seed=0)
+    caps = [int(x) for x in os.environ["P3D_LEVEL_CAPS"].split(",")] if os.environ.get("P3D_LEVEL_CAPS") else None
+    pipe = CenterPointHotPath(cfg, dev, precision=precision, seed=0, level_caps=caps)
     if world > 1:  # weights only: one broadcast over NVLink at start, no per-frame collective
         from paddle3d_b200.sharding import broadcast_weights
         broadcast_weights(pipe.net, 0)

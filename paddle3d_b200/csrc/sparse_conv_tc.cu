@@ -36,8 +36,12 @@ struct Cfg {
   static constexpr int B_STAGE = 2 * B_TILE;      // hi + lo (one cp.async.bulk)
   // two independent rings (<= 96 KB together: two CTAs per SM): SA slots of gathered rows, SB slots of weights.
   // The weight ring is deeper so that the TMA latency never sits on the gather -> MMA critical path.
-  static constexpr int SA = (COUT <= 64) ? 4 : 3;
-  static constexpr int SB_RAW = (96 * 1024 - SA * A_STAGE) / B_STAGE;
+  // Narrow layers (Cout <= 32) have 300-530 row tiles: three CTAs per SM (444 slots) instead of two keeps the
+  // 309-tile 32-channel layers in ONE wave and adds a third MMA-issuing warp per SM.
+  static constexpr int MIN_CTAS = (COUT <= 32) ? 3 : 2;
+  static constexpr int SA = (COUT <= 32) ? 3 : ((COUT <= 64) ? 4 : 3);
+  static constexpr int BUDGET = (COUT <= 32) ? 56 * 1024 : 96 * 1024;  // 3 x (56 K ring + 14 K map + 3 K) <= 228 KB per SM
+  static constexpr int SB_RAW = (BUDGET - SA * A_STAGE) / B_STAGE;
   static constexpr int SB = SB_RAW > 8 ? 8 : SB_RAW;
   static constexpr int RING_BYTES = SA * A_STAGE + SB * B_STAGE;
   // Independent TMEM accumulators: back-to-back tcgen05.mma into ONE accumulator serialise on its dependency
@@ -52,7 +56,7 @@ struct Cfg {
 };
 
 template <int CIN, int COUT>
-__global__ void __launch_bounds__(kThreads, 2) gather_gemm_tf32x3_kernel(const float *__restrict__ in,
+__global__ void __launch_bounds__(kThreads, Cfg<CIN, COUT>::MIN_CTAS) gather_gemm_tf32x3_kernel(const float *__restrict__ in,
                                                                          const int32_t *__restrict__ nbr,
                                                                          const int32_t *__restrict__ n_out_dev,
                                                                          long long n_cap, int K,
