@@ -4,6 +4,7 @@
     VoxelMean            paddle3d/models/voxel_encoders/voxel_encoder.py:42-57
     PointPillarsScatter  paddle3d/models/middle_encoders/pillar_scatter.py:27-105
     SparseResNet3D       paddle3d/models/middle_encoders/sparse_resnet.py:114-206
+    SparseNet3D          paddle3d/models/middle_encoders/sparsenet.py:67-182 (PV-RCNN / Voxel-RCNN family)
 
 Same constructor arguments (the YAML keys stay valid) and the same forward signatures; tensors are
 torch CUDA tensors.  Data-dependent row counts stay on the device: the reference slices by a GPU
@@ -55,11 +56,20 @@ class HardVoxelizer:
         cap = self.max_num_voxels[0] if self.training else self.max_num_voxels[1]
         if isinstance(points, torch.Tensor):
             points = [points]
-        if len(points) != 1:
-            raise NotImplementedError("batch > 1 needs a device-side concat of variable row counts; inference on "
-                                      "this path is batch 1 (docs/models/centerpoint/README.md:107)")
-        v, c, n, nv = self.single_forward(points[0], cap, 0)
-        return VoxelBatch(v, c, n, nv)
+        if len(points) == 1:
+            v, c, n, nv = self.single_forward(points[0], cap, 0)
+            return VoxelBatch(v, c, n, nv)
+        # batch > 1: like the reference (voxelize.py:68-77) each sample is sliced by its own voxel count — one
+        # D2H read per sample — and the pieces are concatenated; the row count of the result is exact.
+        vs, cs, ns = [], [], []
+        for b, p in enumerate(points):
+            v, c, n, nv = self.single_forward(p, cap, b)
+            k = int(nv.item())
+            vs.append(v[:k])
+            cs.append(c[:k])
+            ns.append(n[:k])
+        v, c, n = torch.cat(vs, 0), torch.cat(cs, 0), torch.cat(ns, 0)
+        return VoxelBatch(v, c, n, torch.tensor([v.shape[0]], dtype=torch.int32, device=v.device))
 
     __call__ = forward
 
@@ -190,5 +200,71 @@ class SparseResNet3D:
     def forward(self, voxel_features, coors, batch_size, num=None):
         out, _ = self.forward_sparse(voxel_features, coors, batch_size, num)
         return out.to_dense_bev()  # to_dense + transpose(0,4,1,2,3) + reshape [N, C*D, H, W]
+
+    __call__ = forward
+
+
+class SparseNet3D:
+    """12 sparse convs 16/32/64/64 -> 128 (sparsenet.py:75-111); returns the dense BEV tensor and the four multi-scale
+    sparse tensors that PV-RCNN / Voxel-RCNN consume (sparsenet.py:160-181)."""
+
+    def __init__(self, in_channels=128, voxel_size=(0.2, 0.2, 4), point_cloud_range=(0, -40, -3, 70.4, 40, 1)):
+        self.in_channels = in_channels
+        g = _grid(point_cloud_range, voxel_size)
+        self.sparse_shape = [int(g[2]) + 1, int(g[1]), int(g[0])]
+
+        def cbr(cin, cout, k, stride=1, padding=0, subm=True):
+            conv = (sp.SubmConv3D(cin, cout, k, bias_attr=False) if subm else
+                    sp.Conv3D(cin, cout, k, stride, padding=padding, bias_attr=False))
+            return [conv, sp.BatchNorm(cout, epsilon=1e-3, momentum=1 - 0.01), sp.ReLU()]
+
+        self.conv_input = cbr(in_channels, 16, 3)
+        self.conv1 = [cbr(16, 16, 3)]
+        self.conv2 = [cbr(16, 32, 3, 2, 1, subm=False), cbr(32, 32, 3), cbr(32, 32, 3)]
+        self.conv3 = [cbr(32, 64, 3, 2, 1, subm=False), cbr(64, 64, 3), cbr(64, 64, 3)]
+        self.conv4 = [cbr(64, 64, 3, 2, [0, 1, 1], subm=False), cbr(64, 64, 3), cbr(64, 64, 3)]
+        self.extra_conv = cbr(64, 128, (3, 1, 1), (2, 1, 1), 0, subm=False)
+        self.num_point_features = 128
+        self.backbone_channels = {"x_conv1": 16, "x_conv2": 32, "x_conv3": 64, "x_conv4": 64}
+
+    def sequences(self):
+        return [self.conv_input] + self.conv1 + self.conv2 + self.conv3 + self.conv4 + [self.extra_conv]
+
+    def all_layers(self):
+        return [l for seq in self.sequences() for l in seq[:2]]
+
+    def init_weight(self, seed=0, device="cuda", randomize_bn=False):
+        rng = np.random.default_rng(seed)
+        for l in self.all_layers():
+            if isinstance(l, sp.BatchNorm):
+                l.init_parameters(rng, device, randomize=randomize_bn)
+            else:
+                l.init_parameters(rng, device)
+        return self
+
+    def set_precision(self, precision):
+        for l in self.all_layers():
+            if not isinstance(l, sp.BatchNorm):
+                l.precision = precision
+        return self
+
+    def forward(self, voxel_features, coors, batch_size, num=None):
+        x = sp.sparse_coo_tensor(coors, voxel_features, [batch_size] + self.sparse_shape + [self.in_channels], num=num)
+
+        def run(seqs, t):
+            for seq in seqs:
+                for l in seq:
+                    t = l(t)
+            return t
+
+        x = run([self.conv_input], x)
+        x1 = run(self.conv1, x)
+        x2 = run(self.conv2, x1)
+        x3 = run(self.conv3, x2)
+        x4 = run(self.conv4, x3)
+        out = run([self.extra_conv], x4).to_dense_bev()
+        return {"spatial_features": out, "spatial_features_stride": 8,
+                "multi_scale_3d_features": {"x_conv1": x1, "x_conv2": x2, "x_conv3": x3, "x_conv4": x4},
+                "multi_scale_3d_strides": {"x_conv1": 1, "x_conv2": 2, "x_conv3": 4, "x_conv4": 8}}
 
     __call__ = forward

@@ -140,3 +140,56 @@ def test_sparse_resnet3d_small(cuda, oracle_mod, precision):
     scale = np.abs(want).max()
     np.testing.assert_allclose(got, want, rtol=1e-4, atol=1e-4 * scale)
     assert (want != 0).mean() > 0.05
+
+
+@pytest.mark.parametrize("precision", [0, 1])
+def test_sparsenet3d_small(cuda, oracle_mod, precision):
+    """SparseNet3D (sparsenet.py:67-182): dense BEV output and the multi-scale sparse tensors vs the oracle."""
+    from paddle3d_b200.layers import SparseNet3D
+    cfg = dict(synth.C3, point_cloud_range=[-6.6, -6.6, -5.0, 6.6, 6.6, 3.0])
+    pts = synth.lidar_cloud(dict(cfg, point_cloud_range=[-20, -20, -5, 20, 20, 3]), 8, num_points=30000)
+    v, c, n, nv = oracle_mod.hard_voxelize(pts, cfg["voxel_size"], cfg["point_cloud_range"], 10, 20000)
+    k = int(nv[0])
+    feats = oracle_mod.voxel_mean(v, n, k)
+    coors = np.concatenate([np.zeros((k, 1), np.int32), c[:k]], 1)
+    net = SparseNet3D(5, cfg["voxel_size"], cfg["point_cloud_range"]).init_weight(seed=5, device=cuda, randomize_bn=True)
+    net.set_precision(precision)
+    got = net(_t(cuda, feats), _t(cuda, coors), 1)
+    cc, ff, sp_ = coors, feats, net.sparse_shape
+    scales = []
+    for i, seq in enumerate(net.sequences()):
+        conv, bn = seq[0], seq[1]
+        cc, ff, sp_, _ = oracle_mod.sparse_conv3d(cc, ff, 1, sp_, conv.weight.cpu().numpy(), conv.stride, conv.padding, conv.subm)
+        ff = oracle_mod.bn_relu(ff, bn.weight.cpu().numpy(), bn.bias.cpu().numpy(), bn._mean.cpu().numpy(),
+                                bn._variance.cpu().numpy(), bn.epsilon)
+        if i in (1, 4, 7, 10):
+            scales.append((cc, ff, sp_))
+    want = oracle_mod.sparse_to_dense_bev(cc, ff, 1, sp_)
+    out = got["spatial_features"].cpu().numpy()
+    assert out.shape == want.shape == (1, 256, 22, 22)
+    np.testing.assert_allclose(out, want, rtol=1e-4, atol=1e-4 * np.abs(want).max())
+    for name, (wc, wf, wsp) in zip(["x_conv1", "x_conv2", "x_conv3", "x_conv4"], scales):
+        t = got["multi_scale_3d_features"][name]
+        m = t.nnz()
+        assert m == len(wc) and t.index.spatial == wsp
+        gd = _dense(t.index.coords.cpu().numpy()[:m], t.values().cpu().numpy()[:m], 1, wsp)
+        wd = _dense(wc, wf, 1, wsp)
+        np.testing.assert_allclose(gd, wd, rtol=1e-4, atol=1e-4 * np.abs(wd).max())
+
+
+def test_hard_voxelizer_batch2(cuda, oracle_mod):
+    import torch
+    from paddle3d_b200.layers import HardVoxelizer
+    cfg = synth.C2
+    a, b = synth.lidar_cloud(cfg, 1, num_points=5000), synth.uniform_cloud(cfg, 2, num_points=3000)
+    vx = HardVoxelizer(cfg["voxel_size"], cfg["point_cloud_range"], 8, [4000, 4000])
+    v, c, n = vx([_t(cuda, a), _t(cuda, b)]).trim()
+    wa = oracle_mod.hard_voxelize(a, cfg["voxel_size"], cfg["point_cloud_range"], 8, 4000)
+    wb = oracle_mod.hard_voxelize(b, cfg["voxel_size"], cfg["point_cloud_range"], 8, 4000)
+    ka, kb = int(wa[3][0]), int(wb[3][0])
+    assert v.shape[0] == ka + kb
+    assert np.array_equal(v.cpu().numpy(), np.concatenate([wa[0][:ka], wb[0][:kb]]))
+    cw = np.concatenate([np.concatenate([np.zeros((ka, 1), np.int32), wa[1][:ka]], 1),
+                         np.concatenate([np.ones((kb, 1), np.int32), wb[1][:kb]], 1)])
+    assert np.array_equal(c.cpu().numpy(), cw)
+    assert np.array_equal(n.cpu().numpy(), np.concatenate([wa[2][:ka], wb[2][:kb]]))
