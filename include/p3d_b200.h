@@ -189,6 +189,16 @@ int p3d_sparse_conv_gather_gemm(const float *in, const int32_t *nbr, const int32
                                 const float *shift, const float *residual, int relu, int precision, float *out,
                                 p3d_stream_t stream);
 
+/* Tensor-core gather-GEMM with split-K over the kernel taps for the wide layers (Cout >= 64): layers with few
+ * 128-row tiles are spread over 2 - 3 CTAs per tile; partial sums go to the caller's scratch slabs and are added in a
+ * fixed order by a finalize pass that also applies the epilogue (deterministic).  Same contract as
+ * p3d_sparse_conv_gather_gemm(precision = P3D_CONV_TF32X3); with workspace == NULL it runs unsplit. */
+size_t p3d_sparse_conv_splitk_workspace_bytes(int64_t n_out_cap, int Cin, int Cout);
+int p3d_sparse_conv_gather_gemm_tf32x3_ws(const float *in, const int32_t *nbr, const int32_t *n_out_dev,
+                                          int64_t n_out_cap, int K, int Cin, int Cout, const float *packed_weight,
+                                          const float *scale, const float *shift, const float *residual, int relu,
+                                          float *out, void *workspace, size_t workspace_bytes, p3d_stream_t stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Split-row activations for the tensor-core path.  A "split" row tensor stores every row as its tf32 hi half
  * followed by its tf32 lo half: [n][2][C] fp32 words (x ~= hi + lo, error <= 2^-22 |x|).  Keeping activations in

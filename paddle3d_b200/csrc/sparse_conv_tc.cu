@@ -56,20 +56,20 @@ struct Cfg {
 };
 
 template <int CIN, int COUT>
-__global__ void __launch_bounds__(kThreads, Cfg<CIN, COUT>::MIN_CTAS) gather_gemm_tf32x3_kernel(const float *__restrict__ in,
-                                                                         const int32_t *__restrict__ nbr,
-                                                                         const int32_t *__restrict__ n_out_dev,
-                                                                         long long n_cap, int K,
-                                                                         const float *__restrict__ packed_w,
-                                                                         const float *__restrict__ scale,
-                                                                         const float *__restrict__ shift,
-                                                                         const float *__restrict__ residual, int relu,
-                                                                         float *__restrict__ out) {
+__global__ void __launch_bounds__(kThreads, Cfg<CIN, COUT>::MIN_CTAS)
+    gather_gemm_tf32x3_kernel(const float *__restrict__ in, const int32_t *__restrict__ nbr,
+                              const int32_t *__restrict__ n_out_dev, long long n_cap, int K, int splits,
+                              const float *__restrict__ packed_w, const float *__restrict__ scale,
+                              const float *__restrict__ shift, const float *__restrict__ residual, int relu,
+                              float *__restrict__ out_base) {
   using C = Cfg<CIN, COUT>;
+  // Persistent CTAs: the grid is sized for the SMs (not for the row CAPACITY, which would launch thousands of empty
+  // CTAs) and every CTA walks the work items  w = blockIdx.x, +gridDim.x, ...  with  w = tile * splits + split.
+  // split-K over taps: split s owns the taps t == s (mod splits) and writes raw partial sums to slab s of `out_base`
+  // (the host passes no epilogue parameters then; rows_finalize_kernel adds the slabs in a fixed order).
   const long long n = n_out_dev ? min(static_cast<long long>(n_out_dev[0]), n_cap) : n_cap;
-  const long long row0 = static_cast<long long>(blockIdx.x) * kM;
-  if (row0 >= n) return;
-  const int rows = static_cast<int>(min(static_cast<long long>(kM), n - row0));
+  const long long n_work = ((n + kM - 1) / kM) * splits;
+  if (static_cast<long long>(blockIdx.x) >= n_work) return;
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -83,8 +83,6 @@ __global__ void __launch_bounds__(kThreads, Cfg<CIN, COUT>::MIN_CTAS) gather_gem
   __shared__ uint32_t s_active;                                             // bit t: some row uses tap t (K <= 32)
 
   const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
-  if (tid == 0) s_active = 0u;
-  for (int q = tid; q < kM * K; q += kThreads) s_nbr[q] = (q < rows * K) ? nbr[row0 * K + q] : -1;
   if (tid == kProducers) {  // first lane of the MMA warp
     for (int s = 0; s < C::SA; ++s) {
       mbar_init(smem_u32(&s_bar[kAF + s]), 32);        // the 32 lanes of the slot's producer warp
@@ -107,179 +105,200 @@ __global__ void __launch_bounds__(kThreads, Cfg<CIN, COUT>::MIN_CTAS) gather_gem
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  // which taps does this tile touch at all?
-  if (tid < kProducers) {
-    uint32_t mine = 0u;
-    for (int t = 0; t < K; ++t) mine |= (s_nbr[tid * K + t] >= 0) ? (1u << t) : 0u;
-    mine = __reduce_or_sync(0xffffffffu, mine);
-    if (lane == 0 && mine) atomicOr(&s_active, mine);
-  }
-  __syncthreads();
-  const uint32_t active = s_active;
   const uint32_t tmem_base = s_tmem_base;
-  const int n_stage_uses = __popc(active) * C::G;
 
-  if (wid < 4) {
-    // ------------------------------------------------------------------ producers
-    // Warp w (< STAGES) owns ring slot w: it gathers all 128 rows of its (tap, chunk) uses — lane l takes rows
-    // l, l+32, l+64, l+96, i.e. 4 x CH independent 16-byte loads in flight per lane — so STAGES stages' worth of
-    // L2 gathers are in flight per CTA (two CTAs per SM).
-    const int r = tid;
-    int use = 0;
-    for (int t = 0; t < K; ++t) {
-      if (!((active >> t) & 1u)) continue;
-      for (int g = 0; g < C::G; ++g, ++use) {
-        // Producer warp w owns ring slot w exclusively (uses u = w mod STAGES): with one warp per slot a warp can
-        // never run a full mbarrier phase ahead of the tensor core, so the parity waits cannot alias.
-        const int s = use % C::SA;
-        if (s != wid) continue;
-        const uint32_t ph = static_cast<uint32_t>((use / C::SA) & 1);
-        // lane l gathers rows l, l+32, l+64, l+96 (4 x 64 contiguous bytes): 16 independent 16-byte loads in flight
-        float4 v[4][C::CH];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int src = s_nbr[(lane + 32 * q) * K + t];
-          if (src >= 0) {
-            const float4 *p = reinterpret_cast<const float4 *>(in + static_cast<size_t>(src) * CIN + g * C::KC);
-#pragma unroll
-            for (int c = 0; c < C::CH; ++c) v[q][c] = __ldg(p + c);
-          } else {
-#pragma unroll
-            for (int c = 0; c < C::CH; ++c) v[q][c] = make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-        }
-        mbar_wait(smem_u32(&s_bar[kAE + s]), ph ^ 1u);  // slot free (first pass returns at once)
-        uint8_t *st = a_base + s * C::A_STAGE;
-        // A-tile layout: k-chunk c at c*2048 (LBO), 8-row groups 128 B apart (SBO): the 32 lanes of one store
-        // instruction (32 consecutive rows, same chunk) cover 512 contiguous bytes — no bank conflicts.
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int row = lane + 32 * q;
-          const uint32_t a_off = static_cast<uint32_t>((row >> 3) * 128 + (row & 7) * 16);
-#pragma unroll
-          for (int c = 0; c < C::CH; ++c) {
-            float4 h, l;
-            split_tf32(v[q][c].x, h.x, l.x);
-            split_tf32(v[q][c].y, h.y, l.y);
-            split_tf32(v[q][c].z, h.z, l.z);
-            split_tf32(v[q][c].w, h.w, l.w);
-            *reinterpret_cast<float4 *>(st + c * (kM * 16) + a_off) = h;
-            *reinterpret_cast<float4 *>(st + C::A_TILE + c * (kM * 16) + a_off) = l;
-          }
-        }
-        fence_proxy_async();
-        mbar_arrive(smem_u32(&s_bar[kAF + s]));
+  int use_base = 0;  // pipeline uses consumed by earlier work items of this CTA: the ring phases keep running
+  int item_it = 0;
+  for (long long w = blockIdx.x; w < n_work; w += gridDim.x, ++item_it) {
+    const long long tile = w / splits;
+    const int split = static_cast<int>(w - tile * splits);
+    const long long row0 = tile * kM;
+    const int rows = static_cast<int>(min(static_cast<long long>(kM), n - row0));
+    float *out = out_base + static_cast<size_t>(split) * static_cast<size_t>(n_cap) * COUT;
+    if (tid == 0) s_active = 0u;
+    __syncthreads();  // previous item drained: epilogue finished reading TMEM, s_nbr free
+    {
+      uint32_t mine = 0u;
+      for (int q = tid; q < kM * K; q += kThreads) {
+        const int v = (q < rows * K) ? __ldg(nbr + row0 * K + q) : -1;
+        s_nbr[q] = v;
+        if (v >= 0) mine |= 1u << (q % K);
       }
+      mine = __reduce_or_sync(0xffffffffu, mine);
+      if (lane == 0 && mine) atomicOr(&s_active, mine);
     }
-    // ------------------------------------------------------------------ epilogue
-    mbar_wait(smem_u32(&s_bar[kTF]), 0u);
-    tc_fence_after();
-    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(wid * 32) << 16);
-    const bool live = r < rows;
-    float *orow = out + (row0 + r) * COUT;
-    const float *rrow = residual ? residual + (row0 + r) * COUT : nullptr;
-#pragma unroll 1
-    for (int c0 = 0; c0 < COUT; c0 += 16) {
-      uint32_t a[16];
-      if (n_stage_uses > 0) {
-        asm volatile(
-            "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, "
-            "%15}, [%16];"
-            : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]), "=r"(a[4]), "=r"(a[5]), "=r"(a[6]), "=r"(a[7]), "=r"(a[8]),
-              "=r"(a[9]), "=r"(a[10]), "=r"(a[11]), "=r"(a[12]), "=r"(a[13]), "=r"(a[14]), "=r"(a[15])
-            : "r"(taddr + static_cast<uint32_t>(c0)));
-#pragma unroll
-        for (int acc = 1; acc < C::NACC; ++acc) {
-          uint32_t b[16];
-          asm volatile(
-              "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, "
-              "%15}, [%16];"
-              : "=r"(b[0]), "=r"(b[1]), "=r"(b[2]), "=r"(b[3]), "=r"(b[4]), "=r"(b[5]), "=r"(b[6]), "=r"(b[7]), "=r"(b[8]),
-                "=r"(b[9]), "=r"(b[10]), "=r"(b[11]), "=r"(b[12]), "=r"(b[13]), "=r"(b[14]), "=r"(b[15])
-              : "r"(taddr + static_cast<uint32_t>(acc * COUT + c0)));
-          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-          for (int j = 0; j < 16; ++j) a[j] = __float_as_uint(__uint_as_float(a[j]) + __uint_as_float(b[j]));
-        }
-        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      } else {
-#pragma unroll
-        for (int j = 0; j < 16; ++j) a[j] = 0u;
-      }
-      if (live) {
-        float o[16], res[16];
-        if (rrow) {
-#pragma unroll
-          for (int j = 0; j < 16; j += 4) {
-            const float4 rv = __ldg(reinterpret_cast<const float4 *>(rrow + c0 + j));
-            res[j] = rv.x;
-            res[j + 1] = rv.y;
-            res[j + 2] = rv.z;
-            res[j + 3] = rv.w;
-          }
-        }
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          float v = __uint_as_float(a[j]);
-          if (scale) v = v * __ldg(scale + c0 + j);
-          if (shift) v = v + __ldg(shift + c0 + j);
-          if (rrow) v = v + res[j];
-          if (relu) v = fmaxf(v, 0.f);
-          o[j] = v;
-        }
-#pragma unroll
-        for (int j = 0; j < 16; j += 4)
-          *reinterpret_cast<float4 *>(orow + c0 + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
-      }
+    __syncthreads();
+    uint32_t tap_mask = 0xffffffffu;
+    if (splits > 1) {
+      tap_mask = 0u;
+      for (int t = split; t < K; t += splits) tap_mask |= 1u << t;
     }
-    tc_fence_before();
-  } else if (wid == 4) {
-    // ------------------------------------------------------------------ MMA issuer (warp 4)
-    if (n_stage_uses == 0) {
-      if (lane == 0) mbar_arrive(smem_u32(&s_bar[kTF]));
-    } else {
-      for (int use = 0; use < n_stage_uses; ++use) {
-        const int sa = use % C::SA, sb = use % C::SB;
-        mbar_wait(smem_u32(&s_bar[kBF + sb]), static_cast<uint32_t>((use / C::SB) & 1));
-        mbar_wait(smem_u32(&s_bar[kAF + sa]), static_cast<uint32_t>((use / C::SA) & 1));
-        tc_fence_after();
-        if (lane == 0) {
-          const uint32_t a_hi = smem_u32(a_base + sa * C::A_STAGE), a_lo = a_hi + C::A_TILE;
-          const uint32_t b_hi = smem_u32(b_base + sb * C::B_STAGE), b_lo = b_hi + COUT * 16;  // lo rows follow the hi rows
-#pragma unroll
-          for (int j = 0; j < C::KC / 8; ++j) {
-            const uint32_t ao = static_cast<uint32_t>(2 * j) * (kM * 16), bo = static_cast<uint32_t>(2 * j) * (2 * COUT * 16);
-            const uint64_t dah = smem_desc(a_hi + ao, kM * 16, 128), dal = smem_desc(a_lo + ao, kM * 16, 128);
-            const uint64_t dbh = smem_desc(b_hi + bo, 2 * COUT * 16, 128), dbl = smem_desc(b_lo + bo, 2 * COUT * 16, 128);
-            const uint32_t first = (use | j) ? 1u : 0u;
-            umma_tf32(tmem_base, dal, dbh, C::IDESC, first);                               // acc 0
-            umma_tf32(tmem_base + (C::NACC == 3 ? COUT : 0), dah, dbl, C::IDESC, C::NACC == 3 ? first : 1u);  // acc 1 (or 0)
-            umma_tf32(tmem_base + (C::NACC - 1) * COUT, dah, dbh, C::IDESC, first);         // last acc
-          }
-          umma_commit(smem_u32(&s_bar[kAE + sa]));                             // gathered rows consumed
-          umma_commit(smem_u32(&s_bar[kBE + sb]));                             // weights consumed
-          if (use == n_stage_uses - 1) umma_commit(smem_u32(&s_bar[kTF]));    // accumulator ready
-        }
-        __syncwarp();
-      }
-    }
-    tc_fence_before();
-  } else {
-    // ------------------------------------------------------------------ weight TMA (warp 5, one lane)
-    if (lane == 0) {
-      int use = 0;
+    const uint32_t active = s_active & tap_mask;
+    const int n_stage_uses = __popc(active) * C::G;
+
+    if (wid < 4) {
+      // ---------------------------------------------------------------- producers
+      // Warp w (< SA) owns ring slot w: it gathers all 128 rows of its (tap, chunk) uses — lane l takes rows
+      // l, l+32, l+64, l+96, i.e. 4 x CH independent 16-byte loads in flight per lane — so SA stages' worth of L2
+      // gathers are in flight per CTA.  With one warp per slot a warp can never run a full mbarrier phase ahead of
+      // the tensor core, so the parity waits cannot alias.
+      const int r = tid;
+      int use = use_base;
       for (int t = 0; t < K; ++t) {
         if (!((active >> t) & 1u)) continue;
         for (int g = 0; g < C::G; ++g, ++use) {
-          const int sb = use % C::SB;
-          mbar_wait(smem_u32(&s_bar[kBE + sb]), static_cast<uint32_t>((use / C::SB) & 1) ^ 1u);
-          mbar_arrive_expect_tx(smem_u32(&s_bar[kBF + sb]), static_cast<uint32_t>(C::B_STAGE));
-          bulk_g2s(smem_u32(b_base + sb * C::B_STAGE), packed_w + (static_cast<size_t>(t) * C::G + g) * (2 * C::KC * COUT),
-                   static_cast<uint32_t>(C::B_STAGE), smem_u32(&s_bar[kBF + sb]));
+          const int s = use % C::SA;
+          if (s != wid) continue;
+          const uint32_t ph = static_cast<uint32_t>((use / C::SA) & 1);
+          float4 v[4][C::CH];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int src = s_nbr[(lane + 32 * q) * K + t];
+            if (src >= 0) {
+              const float4 *p = reinterpret_cast<const float4 *>(in + static_cast<size_t>(src) * CIN + g * C::KC);
+#pragma unroll
+              for (int c = 0; c < C::CH; ++c) v[q][c] = __ldg(p + c);
+            } else {
+#pragma unroll
+              for (int c = 0; c < C::CH; ++c) v[q][c] = make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+          }
+          mbar_wait(smem_u32(&s_bar[kAE + s]), ph ^ 1u);  // slot free (first pass returns at once)
+          uint8_t *st = a_base + s * C::A_STAGE;
+          // A-tile layout: k-chunk c at c*2048 (LBO), 8-row groups 128 B apart (SBO): the 32 lanes of one store
+          // instruction (32 consecutive rows, same chunk) cover 512 contiguous bytes — no bank conflicts.
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int row = lane + 32 * q;
+            const uint32_t a_off = static_cast<uint32_t>((row >> 3) * 128 + (row & 7) * 16);
+#pragma unroll
+            for (int c = 0; c < C::CH; ++c) {
+              float4 h, l;
+              split_tf32(v[q][c].x, h.x, l.x);
+              split_tf32(v[q][c].y, h.y, l.y);
+              split_tf32(v[q][c].z, h.z, l.z);
+              split_tf32(v[q][c].w, h.w, l.w);
+              *reinterpret_cast<float4 *>(st + c * (kM * 16) + a_off) = h;
+              *reinterpret_cast<float4 *>(st + C::A_TILE + c * (kM * 16) + a_off) = l;
+            }
+          }
+          fence_proxy_async();
+          mbar_arrive(smem_u32(&s_bar[kAF + s]));
+        }
+      }
+      // ---------------------------------------------------------------- epilogue
+      mbar_wait(smem_u32(&s_bar[kTF]), static_cast<uint32_t>(item_it & 1));
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(wid * 32) << 16);
+      const bool live = r < rows;
+      float *orow = out + (row0 + r) * COUT;
+      const float *rrow = residual ? residual + (row0 + r) * COUT : nullptr;
+#pragma unroll 1
+      for (int c0 = 0; c0 < COUT; c0 += 16) {
+        uint32_t a[16];
+        if (n_stage_uses > 0) {
+          asm volatile(
+              "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, "
+              "%15}, [%16];"
+              : "=r"(a[0]), "=r"(a[1]), "=r"(a[2]), "=r"(a[3]), "=r"(a[4]), "=r"(a[5]), "=r"(a[6]), "=r"(a[7]),
+                "=r"(a[8]), "=r"(a[9]), "=r"(a[10]), "=r"(a[11]), "=r"(a[12]), "=r"(a[13]), "=r"(a[14]), "=r"(a[15])
+              : "r"(taddr + static_cast<uint32_t>(c0)));
+#pragma unroll
+          for (int acc = 1; acc < C::NACC; ++acc) {
+            uint32_t b[16];
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, "
+                "%15}, [%16];"
+                : "=r"(b[0]), "=r"(b[1]), "=r"(b[2]), "=r"(b[3]), "=r"(b[4]), "=r"(b[5]), "=r"(b[6]), "=r"(b[7]),
+                  "=r"(b[8]), "=r"(b[9]), "=r"(b[10]), "=r"(b[11]), "=r"(b[12]), "=r"(b[13]), "=r"(b[14]), "=r"(b[15])
+                : "r"(taddr + static_cast<uint32_t>(acc * COUT + c0)));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < 16; ++j) a[j] = __float_as_uint(__uint_as_float(a[j]) + __uint_as_float(b[j]));
+          }
+          asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) a[j] = 0u;
+        }
+        if (live) {
+          float o[16], res[16];
+          if (rrow) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+              const float4 rv = __ldg(reinterpret_cast<const float4 *>(rrow + c0 + j));
+              res[j] = rv.x;
+              res[j + 1] = rv.y;
+              res[j + 2] = rv.z;
+              res[j + 3] = rv.w;
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float v = __uint_as_float(a[j]);
+            if (scale) v = v * __ldg(scale + c0 + j);
+            if (shift) v = v + __ldg(shift + c0 + j);
+            if (rrow) v = v + res[j];
+            if (relu) v = fmaxf(v, 0.f);
+            o[j] = v;
+          }
+#pragma unroll
+          for (int j = 0; j < 16; j += 4)
+            *reinterpret_cast<float4 *>(orow + c0 + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+        }
+      }
+      tc_fence_before();
+    } else if (wid == 4) {
+      // ---------------------------------------------------------------- MMA issuer (warp 4)
+      if (n_stage_uses == 0) {
+        if (lane == 0) mbar_arrive(smem_u32(&s_bar[kTF]));
+      } else {
+        for (int u = 0; u < n_stage_uses; ++u) {
+          const int use = use_base + u;
+          const int sa = use % C::SA, sb = use % C::SB;
+          mbar_wait(smem_u32(&s_bar[kBF + sb]), static_cast<uint32_t>((use / C::SB) & 1));
+          mbar_wait(smem_u32(&s_bar[kAF + sa]), static_cast<uint32_t>((use / C::SA) & 1));
+          tc_fence_after();
+          if (lane == 0) {
+            const uint32_t a_hi = smem_u32(a_base + sa * C::A_STAGE), a_lo = a_hi + C::A_TILE;
+            const uint32_t b_hi = smem_u32(b_base + sb * C::B_STAGE), b_lo = b_hi + COUT * 16;  // lo rows follow the hi rows
+#pragma unroll
+            for (int j = 0; j < C::KC / 8; ++j) {
+              const uint32_t ao = static_cast<uint32_t>(2 * j) * (kM * 16), bo = static_cast<uint32_t>(2 * j) * (2 * COUT * 16);
+              const uint64_t dah = smem_desc(a_hi + ao, kM * 16, 128), dal = smem_desc(a_lo + ao, kM * 16, 128);
+              const uint64_t dbh = smem_desc(b_hi + bo, 2 * COUT * 16, 128), dbl = smem_desc(b_lo + bo, 2 * COUT * 16, 128);
+              const uint32_t first = (u | j) ? 1u : 0u;
+              umma_tf32(tmem_base, dal, dbh, C::IDESC, first);                               // acc 0
+              umma_tf32(tmem_base + (C::NACC == 3 ? COUT : 0), dah, dbl, C::IDESC, C::NACC == 3 ? first : 1u);  // acc 1 (or 0)
+              umma_tf32(tmem_base + (C::NACC - 1) * COUT, dah, dbh, C::IDESC, first);         // last acc
+            }
+            umma_commit(smem_u32(&s_bar[kAE + sa]));                             // gathered rows consumed
+            umma_commit(smem_u32(&s_bar[kBE + sb]));                             // weights consumed
+            if (u == n_stage_uses - 1) umma_commit(smem_u32(&s_bar[kTF]));      // accumulator ready
+          }
+          __syncwarp();
+        }
+      }
+      tc_fence_before();
+    } else {
+      // ---------------------------------------------------------------- weight TMA (warp 5, one lane)
+      if (lane == 0) {
+        int use = use_base;
+        for (int t = 0; t < K; ++t) {
+          if (!((active >> t) & 1u)) continue;
+          for (int g = 0; g < C::G; ++g, ++use) {
+            const int sb = use % C::SB;
+            mbar_wait(smem_u32(&s_bar[kBE + sb]), static_cast<uint32_t>((use / C::SB) & 1) ^ 1u);
+            mbar_arrive_expect_tx(smem_u32(&s_bar[kBF + sb]), static_cast<uint32_t>(C::B_STAGE));
+            bulk_g2s(smem_u32(b_base + sb * C::B_STAGE), packed_w + (static_cast<size_t>(t) * C::G + g) * (2 * C::KC * COUT),
+                     static_cast<uint32_t>(C::B_STAGE), smem_u32(&s_bar[kBF + sb]));
+          }
         }
       }
     }
+    use_base += n_stage_uses;
   }
+  tc_fence_before();
   __syncthreads();
   if (wid == 4) {
     tc_fence_after();
@@ -311,17 +330,64 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const float *__restri
 
 template <int CIN, int COUT>
 int launch(const float *in, const int32_t *nbr, const int32_t *n_out_dev, int64_t n_cap, int K, const float *packed,
-           const float *scale, const float *shift, const float *residual, int relu, float *out, cudaStream_t st) {
+           const float *scale, const float *shift, const float *residual, int relu, float *out, cudaStream_t st,
+           int splits = 1) {
   using C = Cfg<CIN, COUT>;
   const size_t smem = static_cast<size_t>(C::RING_BYTES) + static_cast<size_t>(kM) * K * sizeof(int32_t) + 1024;
   if (smem > 227 * 1024) return P3D_ERR_UNSUPPORTED;
   auto kern = gather_gemm_tf32x3_kernel<CIN, COUT>;
   P3D_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  kern<<<div_up(n_cap, kM), kThreads, smem, st>>>(in, nbr, n_out_dev, n_cap, K, packed, scale, shift, residual, relu,
+  const long long work = ((n_cap + kM - 1) / kM) * splits;
+  const long long slots = static_cast<long long>(kNumSMs) * C::MIN_CTAS;
+  kern<<<static_cast<unsigned int>(work < slots ? work : slots), kThreads, smem, st>>>(in, nbr, n_out_dev, n_cap, K, splits, packed, scale, shift, residual, relu,
                                                   out);
   P3D_LAUNCH_CHECK();
   return P3D_OK;
 }
+
+// out[r, c] = act((sum_s partial[s][r][c]) * scale + shift (+ residual)), slabs added in index order
+__global__ void __launch_bounds__(256) rows_finalize_kernel(const float *__restrict__ partial, int splits,
+                                                            const int32_t *__restrict__ n_dev, long long n_cap, int C,
+                                                            const float *__restrict__ scale, const float *__restrict__ shift,
+                                                            const float *__restrict__ residual, int relu,
+                                                            float *__restrict__ out) {
+  const long long n = n_dev ? min(static_cast<long long>(n_dev[0]), n_cap) : n_cap;
+  const int c4 = C / 4;
+  const size_t slab = static_cast<size_t>(n_cap) * C / 4;
+  // persistent grid-stride loop over float4s: the grid is sized for the SMs, the trip count follows the device row count
+  for (long long q = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; q < n * c4;
+       q += static_cast<long long>(gridDim.x) * blockDim.x) {
+  const int c = static_cast<int>(q % c4) * 4;
+  const float4 *p = reinterpret_cast<const float4 *>(partial) + q;
+  float4 a = __ldg(p);
+  for (int s = 1; s < splits; ++s) {
+    const float4 b = __ldg(p + s * slab);
+    a.x += b.x;
+    a.y += b.y;
+    a.z += b.z;
+    a.w += b.w;
+  }
+  float v[4] = {a.x, a.y, a.z, a.w};
+  float r[4] = {0.f, 0.f, 0.f, 0.f};
+  if (residual) {
+    const float4 rv = __ldg(reinterpret_cast<const float4 *>(residual) + q);
+    r[0] = rv.x;
+    r[1] = rv.y;
+    r[2] = rv.z;
+    r[3] = rv.w;
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    if (scale) v[j] = v[j] * __ldg(scale + c + j);
+    if (shift) v[j] = v[j] + __ldg(shift + c + j);
+    if (residual) v[j] = v[j] + r[j];
+    if (relu) v[j] = fmaxf(v[j], 0.f);
+  }
+  reinterpret_cast<float4 *>(out)[q] = make_float4(v[0], v[1], v[2], v[3]);
+  }
+}
+
+inline int splits_for(int Cout) { return Cout >= 128 ? 3 : (Cout >= 64 ? 2 : 1); }
 
 }  // namespace tc
 }  // namespace p3d
@@ -344,19 +410,39 @@ extern "C" int p3d_sparse_conv_pack_weights(const float *weight, int K, int Cin,
   return P3D_OK;
 }
 
-extern "C" int p3d_sparse_conv_gather_gemm_tf32x3(const float *in, const int32_t *nbr, const int32_t *n_out_dev,
-                                                  int64_t n_out_cap, int K, int Cin, int Cout, const float *weight,
-                                                  const float *scale, const float *shift, const float *residual,
-                                                  int relu, float *out, p3d_stream_t stream) {
+extern "C" size_t p3d_sparse_conv_splitk_workspace_bytes(int64_t n_out_cap, int Cin, int Cout) {
+  (void)Cin;
+  if (n_out_cap <= 0 || Cout < 16) return 0;
+  const int s = tc::splits_for(Cout);
+  return s > 1 ? align_up(static_cast<size_t>(s) * static_cast<size_t>(n_out_cap) * Cout * sizeof(float)) : 0;
+}
+
+extern "C" int p3d_sparse_conv_gather_gemm_tf32x3_ws(const float *in, const int32_t *nbr, const int32_t *n_out_dev,
+                                                     int64_t n_out_cap, int K, int Cin, int Cout, const float *weight,
+                                                     const float *scale, const float *shift, const float *residual,
+                                                     int relu, float *out, void *workspace, size_t workspace_bytes,
+                                                     p3d_stream_t stream) {
   if (n_out_cap < 0 || K < 1 || K > 32 || !weight || (n_out_cap && (!in || !nbr || !out))) return P3D_ERR_INVALID_ARG;
   if (n_out_cap == 0) return P3D_OK;
   if ((reinterpret_cast<uintptr_t>(in) & 15) || (reinterpret_cast<uintptr_t>(out) & 15) ||
-      (reinterpret_cast<uintptr_t>(weight) & 15))
+      (reinterpret_cast<uintptr_t>(weight) & 15) || (reinterpret_cast<uintptr_t>(residual) & 15) ||
+      (reinterpret_cast<uintptr_t>(workspace) & 15))
     return P3D_ERR_INVALID_ARG;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-#define P3D_TC_CASE(CI, CO)                                                                                    \
-  if (Cin == CI && Cout == CO)                                                                                 \
-    return tc::launch<CI, CO>(in, nbr, n_out_dev, n_out_cap, K, weight, scale, shift, residual, relu, out, st);
+  // Wide layers have few 128-row tiles (52 - 130 at the C3 sizes): split the taps over 2 - 3 CTAs per tile so that all
+  // SMs work on them; needs the scratch slab(s) of p3d_sparse_conv_splitk_workspace_bytes.
+  int splits = tc::splits_for(Cout);
+  if (splits > K) splits = K;
+  const size_t need = static_cast<size_t>(splits) * static_cast<size_t>(n_out_cap) * Cout * sizeof(float);
+  const bool split = splits > 1 && workspace && workspace_bytes >= need;
+  float *conv_out = split ? static_cast<float *>(workspace) : out;
+  const float *k_scale = split ? nullptr : scale, *k_shift = split ? nullptr : shift, *k_res = split ? nullptr : residual;
+  const int k_relu = split ? 0 : relu, k_splits = split ? splits : 1;
+  int rc = P3D_ERR_UNSUPPORTED;
+#define P3D_TC_CASE(CI, CO)                                                                                         \
+  if (Cin == CI && Cout == CO)                                                                                      \
+    rc = tc::launch<CI, CO>(in, nbr, n_out_dev, n_out_cap, K, weight, k_scale, k_shift, k_res, k_relu, conv_out, st, \
+                            k_splits);
   P3D_TC_CASE(16, 16)
   P3D_TC_CASE(16, 32)
   P3D_TC_CASE(32, 32)
@@ -365,5 +451,18 @@ extern "C" int p3d_sparse_conv_gather_gemm_tf32x3(const float *in, const int32_t
   P3D_TC_CASE(64, 128)
   P3D_TC_CASE(128, 128)
 #undef P3D_TC_CASE
-  return P3D_ERR_UNSUPPORTED;
+  if (rc != P3D_OK || !split) return rc;
+  const long long fin_blocks = (n_out_cap * (Cout / 4) + 255) / 256;
+  tc::rows_finalize_kernel<<<static_cast<unsigned int>(fin_blocks < kNumSMs * 8 ? fin_blocks : kNumSMs * 8), 256, 0, st>>>(conv_out, splits, n_out_dev, n_out_cap, Cout,
+                                                                                scale, shift, residual, relu, out);
+  P3D_LAUNCH_CHECK();
+  return P3D_OK;
+}
+
+extern "C" int p3d_sparse_conv_gather_gemm_tf32x3(const float *in, const int32_t *nbr, const int32_t *n_out_dev,
+                                                  int64_t n_out_cap, int K, int Cin, int Cout, const float *weight,
+                                                  const float *scale, const float *shift, const float *residual,
+                                                  int relu, float *out, p3d_stream_t stream) {
+  return p3d_sparse_conv_gather_gemm_tf32x3_ws(in, nbr, n_out_dev, n_out_cap, K, Cin, Cout, weight, scale, shift, residual,
+                                               relu, out, nullptr, 0, stream);
 }

@@ -167,10 +167,17 @@ def _run(p, t, want):
         out = torch.empty((p.cap, p.cout), dtype=torch.float32, device=dev)
         if PROFILE is not None:
             s_ev.record(st)
-        check(L.p3d_sparse_conv_gather_gemm(ptr(xin), ptr(p.nbr), ptr(p.num), p.cap, p.K, p.cin, p.cout,
-                                            ptr(p.weight), ptr(p.scale), ptr(p.shift), ptr(res), int(p.relu),
-                                            1 if p.precision == TF32X3 else 0, ptr(out), stream(dev)),
-              "sparse_conv_gather_gemm")
+        if p.precision == TF32X3:
+            wsb = L.p3d_sparse_conv_splitk_workspace_bytes(p.cap, p.cin, p.cout)  # > 0 for the wide (split-K) layers
+            ws = workspace(wsb, dev, "splitk") if wsb else None
+            check(L.p3d_sparse_conv_gather_gemm_tf32x3_ws(ptr(xin), ptr(p.nbr), ptr(p.num), p.cap, p.K, p.cin, p.cout,
+                                                          ptr(p.weight), ptr(p.scale), ptr(p.shift), ptr(res),
+                                                          int(p.relu), ptr(out), ptr(ws), wsb, stream(dev)),
+                  "sparse_conv_gather_gemm_tf32x3_ws")
+        else:
+            check(L.p3d_sparse_conv_gather_gemm(ptr(xin), ptr(p.nbr), ptr(p.num), p.cap, p.K, p.cin, p.cout,
+                                                ptr(p.weight), ptr(p.scale), ptr(p.shift), ptr(res), int(p.relu), 0,
+                                                ptr(out), stream(dev)), "sparse_conv_gather_gemm")
         t._vals[ROWS_F32] = out
     if PROFILE is not None:
         e_ev.record(st)
