@@ -165,6 +165,23 @@ int p3d_sparse_rulebook_conv(const int32_t *coords, const int32_t *n_in_dev, int
                              const int *pad_host, int32_t *out_coords, int32_t *n_out_dev, int64_t out_cap,
                              int32_t *nbr, void *workspace, size_t workspace_bytes, p3d_stream_t stream);
 
+/* Caller-owned coordinate tables (one per index set / resolution level): the same rulebooks with every level's
+ * table built exactly once per frame.  p3d_sparse_table_build hashes an index set's coordinates;
+ * p3d_sparse_rulebook_subm_t only looks neighbours up in it; p3d_sparse_rulebook_conv_t looks the inputs up in
+ * table_in and leaves in table_out the table of the OUTPUT index set (a by-product of enumerating its sites), ready
+ * for the next stage.  Tables are p3d_sparse_table_bytes(rows_cap) bytes, 16-byte aligned. */
+size_t p3d_sparse_table_bytes(int64_t rows_cap);
+int p3d_sparse_table_build(const int32_t *coords, const int32_t *n_dev, int64_t n_cap, int batch,
+                           const int *spatial_host, void *table, size_t table_bytes, p3d_stream_t stream);
+int p3d_sparse_rulebook_subm_t(const int32_t *coords, const int32_t *n_dev, int64_t n_cap, int batch,
+                               const int *spatial_host, const int *ksize_host, const void *table, size_t table_bytes,
+                               int32_t *nbr, p3d_stream_t stream);
+int p3d_sparse_rulebook_conv_t(const int32_t *coords, const int32_t *n_in_dev, int64_t n_in_cap, int batch,
+                               const int *spatial_host, const int *ksize_host, const int *stride_host,
+                               const int *pad_host, const void *table_in, size_t table_in_bytes, int32_t *out_coords,
+                               int32_t *n_out_dev, int64_t out_cap, void *table_out, size_t table_out_bytes,
+                               int32_t *nbr, p3d_stream_t stream);
+
 /* Unfused elementwise epilogue (BatchNorm(eval) / sparse.add / ReLU on a materialised tensor):
  *   out[r, c] = act(x[r, c] * scale[c] + shift[c] (+ residual[r, c])); out may alias x. */
 int p3d_sparse_affine_act(const float *x, const int32_t *n_dev, int64_t n_cap, int C, const float *scale,

@@ -42,6 +42,11 @@ SIGNATURES = {
     "p3d_sparse_rulebook_subm": (_int, [_vp, _vp, _i64, _int, _vp, _vp, _vp, _vp, _sz, _vp]),
     "p3d_sparse_rulebook_conv": (_int, [_vp, _vp, _i64, _int, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _vp, _sz,
                                         _vp]),
+    "p3d_sparse_table_bytes": (_sz, [_i64]),
+    "p3d_sparse_table_build": (_int, [_vp, _vp, _i64, _int, _vp, _vp, _sz, _vp]),
+    "p3d_sparse_rulebook_subm_t": (_int, [_vp, _vp, _i64, _int, _vp, _vp, _vp, _sz, _vp, _vp]),
+    "p3d_sparse_rulebook_conv_t": (_int, [_vp, _vp, _i64, _int, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _vp, _i64, _vp, _sz,
+                                          _vp, _vp]),
     "p3d_sparse_affine_act": (_int, [_vp, _vp, _i64, _int, _vp, _vp, _vp, _int, _vp, _vp]),
     "p3d_sparse_conv_packed_weight_bytes": (_sz, [_int, _int, _int]),
     "p3d_sparse_conv_pack_weights": (_int, [_vp, _int, _int, _int, _vp, _vp]),

@@ -64,7 +64,10 @@ __device__ __forceinline__ int lookup(const unsigned long long *__restrict__ tab
   while (true) {
     const unsigned long long e = tab[h];
     if (e == kEmpty) return -1;
-    if (static_cast<uint32_t>(e >> 32) == key) return static_cast<int>(static_cast<uint32_t>(e));
+    if (static_cast<uint32_t>(e >> 32) == key) {
+      const uint32_t row = static_cast<uint32_t>(e);
+      return row >= 0x7fffffffu ? -1 : static_cast<int>(row);  // site enumerated beyond the capacity: no row
+    }
     h = (h + 1) & mask;
   }
 }
@@ -155,6 +158,9 @@ __global__ void __launch_bounds__(256) rb_outputs_kernel(const int32_t *__restri
           if (id < out_cap) {
             int4 oc = make_int4(c.x, oz, oy, ox);
             *reinterpret_cast<int4 *>(out_coords + static_cast<size_t>(id) * 4) = oc;
+            // publish the row id: this table doubles as the coordinate table of the OUTPUT index set (same key, one
+            // aligned 8-byte store; concurrent probes only compare the key half)
+            tab_out[h] = (static_cast<unsigned long long>(key) << 32) | static_cast<uint32_t>(id);
           }
           break;
         }
@@ -476,6 +482,100 @@ extern "C" int p3d_sparse_affine_act(const float *x, const int32_t *n_dev, int64
   if (n_cap == 0) return P3D_OK;
   rows_affine_act_kernel<<<div_up(n_cap * C, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       x, n_dev, n_cap, C, scale, shift, residual, relu, out);
+  P3D_LAUNCH_CHECK();
+  return P3D_OK;
+}
+
+// ------------------------------------------------------------------ coordinate tables owned by the caller
+// One table per index set (resolution level).  The level-0 table is built from the voxel coordinates; the table of a
+// strided conv's OUTPUT set is a by-product of enumerating its sites, and is what the next stage's SubM rulebook and
+// the next strided conv look coordinates up in — so every level's table is built exactly once per frame.
+namespace {
+struct Tab {
+  unsigned long long *p;
+  uint32_t cap, shift;
+};
+bool tab_of(void *mem, size_t bytes, int64_t rows_cap, Tab *t) {
+  t->cap = next_pow2(static_cast<uint64_t>(rows_cap > 512 ? rows_cap : 512) * 2);
+  t->shift = 32;
+  for (uint32_t x = t->cap; x > 1; x >>= 1) --t->shift;
+  t->p = static_cast<unsigned long long *>(mem);
+  return mem && bytes >= static_cast<size_t>(t->cap) * 8 && !(reinterpret_cast<uintptr_t>(mem) & 15);
+}
+}  // namespace
+
+extern "C" size_t p3d_sparse_table_bytes(int64_t rows_cap) {
+  if (rows_cap < 0) return 0;
+  return align_up(static_cast<size_t>(next_pow2(static_cast<uint64_t>(rows_cap > 512 ? rows_cap : 512) * 2)) * 8);
+}
+
+extern "C" int p3d_sparse_table_build(const int32_t *coords, const int32_t *n_dev, int64_t n_cap, int batch,
+                                      const int *spatial_host, void *table, size_t table_bytes, p3d_stream_t stream) {
+  const int one[3] = {1, 1, 1};
+  Dims d;
+  int rc = make_dims(batch, spatial_host, one, nullptr, nullptr, 1, &d);
+  if (rc) return rc;
+  Tab t;
+  if (n_cap < 0 || n_cap > 0x7fffffff / 128 || !tab_of(table, table_bytes, n_cap, &t) || (n_cap && !coords) ||
+      (reinterpret_cast<uintptr_t>(coords) & 15))
+    return P3D_ERR_INVALID_ARG;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  P3D_CUDA_CHECK(cudaMemsetAsync(t.p, 0xff, static_cast<size_t>(t.cap) * 8, st));
+  if (n_cap > 0) {
+    rb_insert_kernel<<<div_up(n_cap, 256), 256, 0, st>>>(coords, n_dev, static_cast<int>(n_cap), d, t.p, t.cap - 1, t.shift);
+    P3D_LAUNCH_CHECK();
+  }
+  return P3D_OK;
+}
+
+extern "C" int p3d_sparse_rulebook_subm_t(const int32_t *coords, const int32_t *n_dev, int64_t n_cap, int batch,
+                                          const int *spatial_host, const int *ksize_host, const void *table,
+                                          size_t table_bytes, int32_t *nbr, p3d_stream_t stream) {
+  Dims d;
+  int rc = make_dims(batch, spatial_host, ksize_host, nullptr, nullptr, 1, &d);
+  if (rc) return rc;
+  Tab t;
+  if (n_cap < 0 || n_cap > 0x7fffffff / 128 || !tab_of(const_cast<void *>(table), table_bytes, n_cap, &t) ||
+      (n_cap && (!coords || !nbr)) || (reinterpret_cast<uintptr_t>(coords) & 15))
+    return P3D_ERR_INVALID_ARG;
+  if (n_cap == 0) return P3D_OK;
+  const int K = d.kd * d.kh * d.kw;
+  rb_neighbors_kernel<<<persistent_grid(n_cap * K), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      coords, n_dev, n_cap, d, t.p, t.cap - 1, t.shift, 1, nbr);
+  P3D_LAUNCH_CHECK();
+  return P3D_OK;
+}
+
+extern "C" int p3d_sparse_rulebook_conv_t(const int32_t *coords, const int32_t *n_in_dev, int64_t n_in_cap, int batch,
+                                          const int *spatial_host, const int *ksize_host, const int *stride_host,
+                                          const int *pad_host, const void *table_in, size_t table_in_bytes,
+                                          int32_t *out_coords, int32_t *n_out_dev, int64_t out_cap, void *table_out,
+                                          size_t table_out_bytes, int32_t *nbr, p3d_stream_t stream) {
+  Dims d;
+  int rc = make_dims(batch, spatial_host, ksize_host, stride_host, pad_host, 0, &d);
+  if (rc) return rc;
+  Tab ti, to;
+  if (n_in_cap < 0 || out_cap < 1 || n_in_cap > 0x7fffffff / 128 || out_cap > 0x7fffffff / 128 || !n_out_dev ||
+      !out_coords || !nbr || (n_in_cap && !coords) || !tab_of(const_cast<void *>(table_in), table_in_bytes, n_in_cap, &ti) ||
+      !tab_of(table_out, table_out_bytes, out_cap, &to))
+    return P3D_ERR_INVALID_ARG;
+  if ((reinterpret_cast<uintptr_t>(coords) & 15) || (reinterpret_cast<uintptr_t>(out_coords) & 15))
+    return P3D_ERR_INVALID_ARG;
+  if (static_cast<long long>(batch) * d.oD * d.oH * d.oW >= 0xffffffffll) return P3D_ERR_UNSUPPORTED;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int K = d.kd * d.kh * d.kw;
+  P3D_CUDA_CHECK(cudaMemsetAsync(to.p, 0xff, static_cast<size_t>(to.cap) * 8, st));
+  P3D_CUDA_CHECK(cudaMemsetAsync(n_out_dev, 0, sizeof(int32_t) * 4, st));
+  if (n_in_cap > 0) {
+    rb_outputs_kernel<<<persistent_grid(n_in_cap * K), 256, 0, st>>>(coords, n_in_dev, n_in_cap, d, to.p, to.cap - 1,
+                                                                    to.shift, out_coords, n_out_dev,
+                                                                    static_cast<int>(out_cap));
+    P3D_LAUNCH_CHECK();
+  }
+  rb_finish_kernel<<<1, 1, 0, st>>>(n_out_dev, static_cast<int>(out_cap));
+  P3D_LAUNCH_CHECK();
+  rb_neighbors_kernel<<<persistent_grid(out_cap * K), 256, 0, st>>>(out_coords, n_out_dev, out_cap, d, ti.p, ti.cap - 1,
+                                                                   ti.shift, 0, nbr);
   P3D_LAUNCH_CHECK();
   return P3D_OK;
 }

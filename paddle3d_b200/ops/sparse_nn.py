@@ -43,11 +43,23 @@ def _triple(v):
 
 
 class _IndexSet:
-    """Active sites of one resolution level: coords [cap, 4] (b, z, y, x), device count, rulebooks."""
+    """Active sites of one resolution level: coords [cap, 4] (b, z, y, x), device count, its coordinate hash table
+    (built once: from the coordinates for the input level, as a by-product of the site enumeration for the output of a
+    strided conv) and the SubM rulebooks that share it."""
 
-    def __init__(self, coords, num, cap, batch, spatial):
+    def __init__(self, coords, num, cap, batch, spatial, table=None):
         self.coords, self.num, self.cap, self.batch, self.spatial = coords, num, cap, batch, list(spatial)
         self.subm_rulebooks = {}
+        self._table = table
+
+    def table(self):
+        if self._table is None:
+            L = lib()
+            dev = self.coords.device
+            self._table = torch.empty((L.p3d_sparse_table_bytes(self.cap),), dtype=torch.uint8, device=dev)
+            check(L.p3d_sparse_table_build(ptr(self.coords), ptr(self.num), self.cap, self.batch, host_ints(self.spatial),
+                                           ptr(self._table), self._table.numel(), stream(dev)), "sparse_table_build")
+        return self._table
 
     def subm_rulebook(self, ksize, key):
         k = (key, tuple(ksize)) if key is not None else ("_anon", tuple(ksize))
@@ -56,11 +68,10 @@ class _IndexSet:
             K = ksize[0] * ksize[1] * ksize[2]
             dev = self.coords.device
             nbr = torch.empty((self.cap, K), dtype=torch.int32, device=dev)
-            L = lib()
-            ws = workspace(L.p3d_sparse_rulebook_workspace_bytes(self.cap, 0), dev, "rulebook")
-            check(L.p3d_sparse_rulebook_subm(ptr(self.coords), ptr(self.num), self.cap, self.batch,
-                                             host_ints(self.spatial), host_ints(ksize), ptr(nbr), ptr(ws), ws.numel(),
-                                             stream(dev)), "sparse_rulebook_subm")
+            tab = self.table()
+            check(lib().p3d_sparse_rulebook_subm_t(ptr(self.coords), ptr(self.num), self.cap, self.batch,
+                                                   host_ints(self.spatial), host_ints(ksize), ptr(tab), tab.numel(),
+                                                   ptr(nbr), stream(dev)), "sparse_rulebook_subm_t")
             self.subm_rulebooks[k] = nbr
         return nbr
 
@@ -287,13 +298,15 @@ class _ConvBase(_Layer):
             n_out = torch.empty((4,), dtype=torch.int32, device=dev)
             nbr = torch.empty((cap, K), dtype=torch.int32, device=dev)
             L = lib()
-            ws = workspace(L.p3d_sparse_rulebook_workspace_bytes(src.cap, cap), dev, "rulebook")
-            check(L.p3d_sparse_rulebook_conv(ptr(src.coords), ptr(src.num), src.cap, src.batch, host_ints(src.spatial),
-                                             host_ints(self.kernel_size), host_ints(self.stride),
-                                             host_ints(self.padding), ptr(out_coords), ptr(n_out), cap, ptr(nbr),
-                                             ptr(ws), ws.numel(), stream(dev)), "sparse_rulebook_conv")
+            tab_in = src.table()
+            tab_out = torch.empty((L.p3d_sparse_table_bytes(cap),), dtype=torch.uint8, device=dev)
+            check(L.p3d_sparse_rulebook_conv_t(ptr(src.coords), ptr(src.num), src.cap, src.batch, host_ints(src.spatial),
+                                               host_ints(self.kernel_size), host_ints(self.stride),
+                                               host_ints(self.padding), ptr(tab_in), tab_in.numel(), ptr(out_coords),
+                                               ptr(n_out), cap, ptr(tab_out), tab_out.numel(), ptr(nbr), stream(dev)),
+                  "sparse_rulebook_conv_t")
             osp = [(src.spatial[a] + 2 * self.padding[a] - self.kernel_size[a]) // self.stride[a] + 1 for a in range(3)]
-            index = _IndexSet(out_coords, n_out, cap, src.batch, osp)
+            index = _IndexSet(out_coords, n_out, cap, src.batch, osp, table=tab_out)
             index.counters = n_out
             p.nbr = nbr
         p.num, p.cap = index.num, index.cap

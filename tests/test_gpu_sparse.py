@@ -193,3 +193,32 @@ def test_hard_voxelizer_batch2(cuda, oracle_mod):
                          np.concatenate([np.ones((kb, 1), np.int32), wb[1][:kb]], 1)])
     assert np.array_equal(c.cpu().numpy(), cw)
     assert np.array_equal(n.cpu().numpy(), np.concatenate([wa[2][:ka], wb[2][:kb]]))
+
+
+def test_workspace_and_table_rulebook_apis_agree(cuda):
+    """The scratch-workspace rulebook entry point (p3d_sparse_rulebook_subm) and the caller-owned-table one
+    (p3d_sparse_table_build + p3d_sparse_rulebook_subm_t) must produce the same neighbour map."""
+    import torch
+    from paddle3d_b200._lib import check, host_ints, lib
+    from paddle3d_b200._mem import ptr, stream
+    from paddle3d_b200.ops import sparse_nn as sp
+    rng = np.random.default_rng(4)
+    coords = _rand_sites(rng, 2, 9, 33, 31, 0.1)
+    n = len(coords)
+    x = sp.sparse_coo_tensor(_t(cuda, coords).t(), _t(cuda, rng.normal(size=(n, 16)).astype(np.float32)), [2, 9, 33, 31, 16])
+    a = x.index.subm_rulebook([3, 3, 3], "k")
+    L = lib()
+    ws = torch.empty((L.p3d_sparse_rulebook_workspace_bytes(n, 0),), dtype=torch.uint8, device=cuda)
+    b = torch.empty((n, 27), dtype=torch.int32, device=cuda)
+    check(L.p3d_sparse_rulebook_subm(ptr(x.index.coords), None, n, 2, host_ints([9, 33, 31]), host_ints([3, 3, 3]), ptr(b),
+                                     ptr(ws), ws.numel(), stream(cuda)), "rulebook_subm")
+    assert torch.equal(a, b)
+    # every entry points at the row whose coordinate is coord + offset
+    nb = a.cpu().numpy()
+    k = 0
+    for dz in (-1, 0, 1):
+        for dy in (-1, 0, 1):
+            for dx in (-1, 0, 1):
+                rows = np.nonzero(nb[:, k] >= 0)[0]
+                assert np.array_equal(coords[nb[rows, k]], coords[rows] + np.array([0, dz, dy, dx], np.int32))
+                k += 1
