@@ -226,6 +226,9 @@ int p3d_sparse_conv_gather_gemm_tf32x3_ws(const float *in, const int32_t *nbr, c
  *     in_split [n_in][2][Cin], residual_split [n_out][2][Cout] or NULL, packed weights
  *     (p3d_sparse_conv_pack_weights), and out_f32 [n_out, Cout] and / or out_split [n_out][2][Cout] (either may be
  *     NULL, not both).  Persistent grid sized to the device row count.
+ *   p3d_sparse_conv_gather_gemm_split_ws: the same with a scratch buffer of
+ *     p3d_sparse_conv_splitk_workspace_bytes(n_out_cap, Cin, Cout) bytes; when present the wide layers run split-K over
+ *     taps (partial sums in the scratch slabs, added in slab order by a finalize kernel: deterministic).
  * ------------------------------------------------------------------------------------------- */
 int p3d_rows_convert_layout(const float *src, int src_layout, const int32_t *n_dev, int64_t n_cap, int C, float *dst,
                             p3d_stream_t stream);
@@ -233,6 +236,11 @@ int p3d_sparse_conv_gather_gemm_split(const float *in_split, const int32_t *nbr,
                                       int64_t n_out_cap, int K, int Cin, int Cout, const float *packed_weight,
                                       const float *scale, const float *shift, const float *residual_split, int relu,
                                       float *out_f32, float *out_split, p3d_stream_t stream);
+int p3d_sparse_conv_gather_gemm_split_ws(const float *in_split, const int32_t *nbr, const int32_t *n_out_dev,
+                                         int64_t n_out_cap, int K, int Cin, int Cout, const float *packed_weight,
+                                         const float *scale, const float *shift, const float *residual_split, int relu,
+                                         float *out_f32, float *out_split, void *workspace, size_t workspace_bytes,
+                                         p3d_stream_t stream);
 
 #ifdef __cplusplus
 }

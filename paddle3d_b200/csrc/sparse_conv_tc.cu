@@ -20,8 +20,6 @@
 // Taps that no row of the tile uses are skipped for the whole tile (block-uniform bitmask).
 // Weights are packed once per layer by p3d_sparse_conv_pack_weights into exactly the shared-memory image:
 //   packed[tap][chunk g][hi|lo][KC/4 k-chunks][Cout rows][4 floats].
-#include <stdlib.h>
-
 #include "tc_common.cuh"
 
 namespace p3d {
@@ -389,14 +387,6 @@ __global__ void __launch_bounds__(256) rows_finalize_kernel(const float *__restr
   }
 }
 
-inline int splits_for(int Cout) {
-  // tuning hooks (not a public knob): P3D_SPLITS_128 / P3D_SPLITS_64 / P3D_SPLITS_32 override the defaults
-  static const int s128 = getenv("P3D_SPLITS_128") ? atoi(getenv("P3D_SPLITS_128")) : 3;
-  static const int s64 = getenv("P3D_SPLITS_64") ? atoi(getenv("P3D_SPLITS_64")) : 2;
-  static const int s32 = getenv("P3D_SPLITS_32") ? atoi(getenv("P3D_SPLITS_32")) : 1;
-  const int v = Cout >= 128 ? s128 : (Cout >= 64 ? s64 : s32);
-  return v < 1 ? 1 : (v > 8 ? 8 : v);
-}
 
 }  // namespace tc
 }  // namespace p3d

@@ -26,17 +26,17 @@ struct Cfg {
   // One pipeline "use" = one tap x KC input channels for the CTA's 128 rows.  Every use costs ~800 cycles of
   // fixed skeleton time in the single MMA-issuing warp (barrier wait, fences, commit — measured in-kernel with
   // gathers, weight copies and MMAs all disabled), so uses are made as large as shared memory allows.
-  static constexpr int KC = (CIN >= 64) ? 32 : 16;
+  static constexpr int KC = (CIN >= 32) ? 32 : 16;        // 32 channels = one full 128-byte line per gathered row half
   static constexpr int G = CIN / KC;
   static constexpr int CH = KC / 4;                      // 16-byte k-chunks per use
   static constexpr int A_TILE = KC * kM * 4;             // one of hi / lo
   static constexpr int A_STAGE = 2 * A_TILE;
   static constexpr int B_STAGE = 2 * KC * COUT * 4;      // [chunk][hi rows | lo rows][16 B]
   static constexpr int STAGE = A_STAGE + B_STAGE;        // ONE ring: rows and weights of a use share a slot
-  static constexpr int BUDGET = (COUT <= 32) ? 100 * 1024 : 192 * 1024;   // two CTAs per SM for the narrow layers
+  static constexpr int BUDGET = (COUT <= 64) ? 100 * 1024 : 192 * 1024;   // two CTAs per SM except for Cout = 128
   static constexpr int S_RAW = BUDGET / STAGE;
   static constexpr int STAGES = S_RAW > 8 ? 8 : (S_RAW < 2 ? 2 : S_RAW);
-  static constexpr int MIN_CTAS = (COUT <= 32) ? 2 : 1;
+  static constexpr int MIN_CTAS = (COUT <= 64) ? 2 : 1;
   // Two MMAs per 8-wide k-step: [B_hi | B_lo] is one K-major operand of 2*Cout rows, so
   //   acc[0 .. 2N)   += A_hi x [B_hi | B_lo]      (N' = 2*Cout)
   //   acc[2N .. 3N)  += A_lo x B_hi               (N  = Cout)
@@ -62,6 +62,29 @@ __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, bool v
 __device__ __forceinline__ void cp_async_arrive_noinc(uint32_t bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }
+// K-major SWIZZLE_128B operand: rows of 128 bytes (32 tf32), 8-row atoms of 1024 bytes (SBO), the 16-byte chunk index
+// of a row XOR-ed with (row & 7).  Tile base 1024-byte aligned; a k-step advances the start address by 32 bytes.
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((addr & 0x3ffffu) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;            // LBO: unused for swizzled K-major, canonical value 1
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;    // SBO
+  d |= 1ull << 46;                                // descriptor version 1
+  d |= 2ull << 61;                                // layout type SWIZZLE_128B
+  return d;
+}
+
+// K-major SWIZZLE_64B operand: rows of 64 bytes (16 tf32), 8-row atoms of 512 bytes (SBO), chunk ^= (row >> 1) & 3.
+__device__ __forceinline__ uint64_t smem_desc_sw64(uint32_t addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((addr & 0x3ffffu) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(512 >> 4) << 32;
+  d |= 1ull << 46;
+  d |= 4ull << 61;  // layout type SWIZZLE_64B
+  return d;
+}
+
 // Warp-uniform issue: every lane executes the instruction stream (so the descriptors stay in uniform registers
 // instead of going through a per-MMA R2UR waterfall), one elected lane issues.
 __device__ __forceinline__ void umma_tf32_elect(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
@@ -85,7 +108,7 @@ __device__ __forceinline__ void umma_commit_elect(uint32_t bar) {
 template <int CIN, int COUT>
 __global__ void __launch_bounds__(kThreads, Cfg<CIN, COUT>::MIN_CTAS)
     gather_gemm_split_kernel(const float *__restrict__ in_split, const int32_t *__restrict__ nbr,
-                             const int32_t *__restrict__ n_out_dev, long long n_cap, int K,
+                             const int32_t *__restrict__ n_out_dev, long long n_cap, int K, int splits,
                              const float *__restrict__ packed_w, const float *__restrict__ scale,
                              const float *__restrict__ shift, const float *__restrict__ residual_split, int relu,
                              float *__restrict__ out_f32, float *__restrict__ out_split, long long *__restrict__ dbg) {
@@ -94,7 +117,10 @@ __global__ void __launch_bounds__(kThreads, Cfg<CIN, COUT>::MIN_CTAS)
   //   5 MMA: slot full               6 MMA: issued + committed
   using C = Cfg<CIN, COUT>;
   const long long n = n_out_dev ? min(static_cast<long long>(n_out_dev[0]), n_cap) : n_cap;
-  if (static_cast<long long>(blockIdx.x) * kM >= n) return;
+  // work items w = tile * splits + split; split s owns the taps t == s (mod splits) and, when splits > 1, writes raw
+  // partial sums to slab s of out_f32 (the caller passes the scratch slabs and no epilogue operands).
+  const long long n_work = ((n + kM - 1) / kM) * splits;
+  if (static_cast<long long>(blockIdx.x) >= n_work) return;
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -128,7 +154,15 @@ __global__ void __launch_bounds__(kThreads, Cfg<CIN, COUT>::MIN_CTAS)
 
   int use_base = 0;  // pipeline uses consumed by earlier tiles of this CTA (ring phases keep running)
   int tile_it = 0;
-  for (long long tile = blockIdx.x; tile * kM < n; tile += gridDim.x, ++tile_it) {
+  for (long long w = blockIdx.x; w < n_work; w += gridDim.x, ++tile_it) {
+    const long long tile = w / splits;
+    const int split = static_cast<int>(w - tile * splits);
+    float *out_rows = out_f32 ? out_f32 + static_cast<size_t>(split) * static_cast<size_t>(n_cap) * COUT : nullptr;
+    uint32_t tap_mask = 0xffffffffu;
+    if (splits > 1) {
+      tap_mask = 0u;
+      for (int t = split; t < K; t += splits) tap_mask |= 1u << t;
+    }
     const long long row0 = tile * kM;
     const int rows = static_cast<int>(min(static_cast<long long>(kM), n - row0));
     if (tid == 0) s_active = 0u;
@@ -144,7 +178,7 @@ __global__ void __launch_bounds__(kThreads, Cfg<CIN, COUT>::MIN_CTAS)
       if (lane == 0 && mine) atomicOr(&s_active, mine);
     }
     __syncthreads();
-    const uint32_t active = s_active;
+    const uint32_t active = s_active & tap_mask;
     const int n_uses = __popc(active) * C::G;
     const int flags = dbg ? g_dbg_flags : 0;  // only the debug entry point passes dbg
 
@@ -153,35 +187,63 @@ __global__ void __launch_bounds__(kThreads, Cfg<CIN, COUT>::MIN_CTAS)
       // a warp instruction covers 8 rows x 4 k-chunks: 64 contiguous bytes per gathered row, 512 contiguous bytes of
       // shared memory (A tile: k-chunk stride LBO = 128 B inside a 4-chunk block, 8-row groups SBO = 512 B apart,
       // 16-channel blocks 8 KB apart).
-      const int sub = lane >> 2, ch = lane & 3;
       int use = use_base;
       for (int t = 0; t < K; ++t) {
         if (!((active >> t) & 1u)) continue;
-        int src[4];
+        if (C::KC == 32) {
+          // FULL-LINE gathers (measured 36-72 B/clk/SM vs 11-19 for 64-byte pieces, tools/gather_microbench.cu):
+          // 8 lanes fetch the 128 contiguous bytes (32 channels) of one row half, a warp instruction covers 4 rows;
+          // destination = SWIZZLE_128B tile (row pitch 128 B, chunk ^= row & 7): 512 contiguous bytes, no conflicts.
+          const int sub = lane >> 3, ch = lane & 7;
+          int src[8];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) src[q] = s_nbr[(wid * 32 + q * 8 + sub) * K + t];
-        for (int g = 0; g < C::G; ++g, ++use) {
-          const int s = use % C::STAGES;
-          mbar_wait(smem_u32(&s_bar[kE + s]), (static_cast<uint32_t>(use / C::STAGES) & 1u) ^ 1u);
-          if (dbg && blockIdx.x == 0 && tid == 0 && use < 512) dbg[use * 8 + 0] = clock64();
-          const uint32_t st = ring + static_cast<uint32_t>(s * C::STAGE);
+          for (int q = 0; q < 8; ++q) src[q] = s_nbr[(wid * 32 + q * 4 + sub) * K + t];
+          for (int g = 0; g < C::G; ++g, ++use) {
+            const int s = use % C::STAGES;
+            mbar_wait(smem_u32(&s_bar[kE + s]), (static_cast<uint32_t>(use / C::STAGES) & 1u) ^ 1u);
+            if (dbg && blockIdx.x == 0 && tid == 0 && use < 512) dbg[use * 8 + 0] = clock64();
+            const uint32_t st = ring + static_cast<uint32_t>(s * C::STAGE);
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const bool ok = src[q] >= 0;
-            const float *p = in_split + (ok ? static_cast<size_t>(src[q]) * (2 * CIN) : 0) + g * C::KC + ch * 4;
-            const uint32_t d = st + static_cast<uint32_t>((wid * 4 + q) * 512 + ch * 128 + sub * 16);
-#pragma unroll
-            for (int b = 0; b < C::KC / 16; ++b) {  // 16-channel blocks of this use
+            for (int q = 0; q < 8; ++q) {
+              const bool ok = src[q] >= 0;
+              const int row = wid * 32 + q * 4 + sub;
+              const float *p = in_split + (ok ? static_cast<size_t>(src[q]) * (2 * CIN) : 0) + g * 32 + ch * 4;
+              const uint32_t d = st + static_cast<uint32_t>(row * 128 + ((ch ^ (row & 7)) << 4));
               if (flags & 2) continue;
-              cp_async16(d + b * (kM * 64), p + b * 16, ok);                    // hi
-              cp_async16(d + b * (kM * 64) + C::A_TILE, p + b * 16 + CIN, ok);  // lo
+              cp_async16(d, p, ok);                       // hi
+              cp_async16(d + C::A_TILE, p + CIN, ok);     // lo
             }
+            if (flags & 32)
+              mbar_arrive(smem_u32(&s_bar[kF + s]));
+            else
+              cp_async_arrive_noinc(smem_u32(&s_bar[kF + s]));
+            if (dbg && blockIdx.x == 0 && tid == 0 && use < 512) dbg[use * 8 + 1] = clock64();
           }
-          if (flags & 32)
-            mbar_arrive(smem_u32(&s_bar[kF + s]));
-          else
-            cp_async_arrive_noinc(smem_u32(&s_bar[kF + s]));
-          if (dbg && blockIdx.x == 0 && tid == 0 && use < 512) dbg[use * 8 + 1] = clock64();
+        } else {
+          // 16-channel layers: a split row [hi 16 | lo 16] is ONE 128-byte line: 8 lanes fetch it (lanes 0-3 the hi
+          // chunks, 4-7 the lo chunks), a warp instruction covers 4 rows; tiles are SWIZZLE_64B (row pitch 64 B).
+          const int sub = lane >> 3, ch = lane & 3, part = (lane >> 2) & 1;
+          int src[8];
+#pragma unroll
+          for (int q = 0; q < 8; ++q) src[q] = s_nbr[(wid * 32 + q * 4 + sub) * K + t];
+          for (int g = 0; g < C::G; ++g, ++use) {
+            const int s = use % C::STAGES;
+            mbar_wait(smem_u32(&s_bar[kE + s]), (static_cast<uint32_t>(use / C::STAGES) & 1u) ^ 1u);
+            const uint32_t st = ring + static_cast<uint32_t>(s * C::STAGE);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const bool ok = src[q] >= 0;
+              const int row = wid * 32 + q * 4 + sub;
+              const float *p = in_split + (ok ? static_cast<size_t>(src[q]) * (2 * CIN) : 0) + part * CIN + g * 16 + ch * 4;
+              const uint32_t d = st + static_cast<uint32_t>(part * C::A_TILE + row * 64 + ((ch ^ ((row >> 1) & 3)) << 4));
+              if (flags & 2) continue;
+              cp_async16(d, p, ok);
+            }
+            if (flags & 32)
+              mbar_arrive(smem_u32(&s_bar[kF + s]));
+            else
+              cp_async_arrive_noinc(smem_u32(&s_bar[kF + s]));
+          }
         }
       }
       // ---------------------------------------------------------------- epilogue
@@ -241,10 +303,10 @@ __global__ void __launch_bounds__(kThreads, Cfg<CIN, COUT>::MIN_CTAS)
             if (relu) v = fmaxf(v, 0.f);
             o[j] = v;
           }
-          if (out_f32) {
+          if (out_rows) {
 #pragma unroll
             for (int j = 0; j < 16; j += 4)
-              *reinterpret_cast<float4 *>(out_f32 + orow * COUT + c0 + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+              *reinterpret_cast<float4 *>(out_rows + orow * COUT + c0 + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
           }
           if (out_split) {
             float h[16], l[16];
@@ -277,9 +339,15 @@ __global__ void __launch_bounds__(kThreads, Cfg<CIN, COUT>::MIN_CTAS)
 #pragma unroll
           for (int j = 0; j < C::KC / 8; ++j) {
             // k-step j: 16-channel block j / 2, chunk pair (j & 1) inside it
-            const uint32_t ao = static_cast<uint32_t>(j >> 1) * (kM * 64) + static_cast<uint32_t>(j & 1) * 256;
             const uint32_t bo = static_cast<uint32_t>(2 * j) * (2 * COUT * 16);
-            const uint64_t dah = smem_desc(a_hi + ao, 128, 512), dal = smem_desc(a_lo + ao, 128, 512);
+            uint64_t dah, dal;
+            if (C::KC == 32) {  // SWIZZLE_128B tiles: k-step j starts 32 bytes further into the 128-byte rows
+              dah = smem_desc_sw128(a_hi + j * 32);
+              dal = smem_desc_sw128(a_lo + j * 32);
+            } else {            // SWIZZLE_64B tiles (16-channel layers)
+              dah = smem_desc_sw64(a_hi + j * 32);
+              dal = smem_desc_sw64(a_lo + j * 32);
+            }
             const uint64_t db = smem_desc(b_all + bo, 2 * COUT * 16, 128);  // rows 0..N-1 = hi, N..2N-1 = lo
             const uint32_t first = (u | j) ? 1u : 0u;
             if (flags & 4) continue;
@@ -338,19 +406,70 @@ __global__ void __launch_bounds__(kThreads, Cfg<CIN, COUT>::MIN_CTAS)
 template <int CIN, int COUT>
 int launch(const float *in_split, const int32_t *nbr, const int32_t *n_out_dev, int64_t n_cap, int K,
            const float *packed, const float *scale, const float *shift, const float *residual_split, int relu,
-           float *out_f32, float *out_split, cudaStream_t st, long long *dbg = nullptr) {
+           float *out_f32, float *out_split, cudaStream_t st, long long *dbg = nullptr, int splits = 1) {
   using C = Cfg<CIN, COUT>;
   const size_t smem = static_cast<size_t>(C::STAGES) * C::STAGE + static_cast<size_t>(kM) * K * sizeof(int32_t) + 1024;
   if (smem > 227 * 1024) return P3D_ERR_UNSUPPORTED;
   auto kern = gather_gemm_split_kernel<CIN, COUT>;
   P3D_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-  const long long tiles = (n_cap + kM - 1) / kM;
+  const long long work = ((n_cap + kM - 1) / kM) * splits;
   const long long slots = static_cast<long long>(kNumSMs) * C::MIN_CTAS;
-  const unsigned int grid = static_cast<unsigned int>(tiles < slots ? tiles : slots);
-  kern<<<grid, kThreads, smem, st>>>(in_split, nbr, n_out_dev, n_cap, K, packed, scale, shift, residual_split, relu,
+  const unsigned int grid = static_cast<unsigned int>(work < slots ? work : slots);
+  kern<<<grid, kThreads, smem, st>>>(in_split, nbr, n_out_dev, n_cap, K, splits, packed, scale, shift, residual_split, relu,
                                      out_f32, out_split, dbg);
   P3D_LAUNCH_CHECK();
   return P3D_OK;
+}
+
+// split-K finalize: v = act((sum_s partial[s][r][c]) * scale + shift (+ residual)), slabs added in index order; the
+// residual comes in the split layout and the result goes out as fp32 rows and / or split rows.
+__global__ void __launch_bounds__(256)
+    rows_finalize_split_kernel(const float *__restrict__ partial, int splits, const int32_t *__restrict__ n_dev,
+                               long long n_cap, int C, const float *__restrict__ scale, const float *__restrict__ shift,
+                               const float *__restrict__ residual_split, int relu, float *__restrict__ out_f32,
+                               float *__restrict__ out_split) {
+  const long long n = n_dev ? min(static_cast<long long>(n_dev[0]), n_cap) : n_cap;
+  const int c4 = C / 4;
+  const size_t slab = static_cast<size_t>(n_cap) * C / 4;
+  for (long long q = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; q < n * c4;
+       q += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const long long r = q / c4;
+    const int c = static_cast<int>(q - r * c4) * 4;
+    const float4 *p = reinterpret_cast<const float4 *>(partial) + q;
+    float4 a = __ldg(p);
+    for (int s = 1; s < splits; ++s) {
+      const float4 b = __ldg(p + s * slab);
+      a.x += b.x;
+      a.y += b.y;
+      a.z += b.z;
+      a.w += b.w;
+    }
+    float v[4] = {a.x, a.y, a.z, a.w};
+    float res[4] = {0.f, 0.f, 0.f, 0.f};
+    if (residual_split) {
+      const float4 h = __ldg(reinterpret_cast<const float4 *>(residual_split + r * 2 * C + c));
+      const float4 l = __ldg(reinterpret_cast<const float4 *>(residual_split + r * 2 * C + C + c));
+      res[0] = h.x + l.x;
+      res[1] = h.y + l.y;
+      res[2] = h.z + l.z;
+      res[3] = h.w + l.w;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (scale) v[j] = v[j] * __ldg(scale + c + j);
+      if (shift) v[j] = v[j] + __ldg(shift + c + j);
+      if (residual_split) v[j] = v[j] + res[j];
+      if (relu) v[j] = fmaxf(v[j], 0.f);
+    }
+    if (out_f32) reinterpret_cast<float4 *>(out_f32)[q] = make_float4(v[0], v[1], v[2], v[3]);
+    if (out_split) {
+      float h[4], l[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) split_tf32(v[j], h[j], l[j]);
+      *reinterpret_cast<float4 *>(out_split + r * 2 * C + c) = make_float4(h[0], h[1], h[2], h[3]);
+      *reinterpret_cast<float4 *>(out_split + r * 2 * C + C + c) = make_float4(l[0], l[1], l[2], l[3]);
+    }
+  }
 }
 
 // rows [n, C] fp32 <-> split rows [n][2][C]
@@ -394,22 +513,34 @@ extern "C" int p3d_rows_convert_layout(const float *src, int src_layout, const i
   return P3D_OK;
 }
 
-extern "C" int p3d_sparse_conv_gather_gemm_split(const float *in_split, const int32_t *nbr, const int32_t *n_out_dev,
-                                                 int64_t n_out_cap, int K, int Cin, int Cout, const float *packed_weight,
-                                                 const float *scale, const float *shift, const float *residual_split,
-                                                 int relu, float *out_f32, float *out_split, p3d_stream_t stream) {
+extern "C" int p3d_sparse_conv_gather_gemm_split_ws(const float *in_split, const int32_t *nbr,
+                                                    const int32_t *n_out_dev, int64_t n_out_cap, int K, int Cin,
+                                                    int Cout, const float *packed_weight, const float *scale,
+                                                    const float *shift, const float *residual_split, int relu,
+                                                    float *out_f32, float *out_split, void *workspace,
+                                                    size_t workspace_bytes, p3d_stream_t stream) {
   if (n_out_cap < 0 || K < 1 || K > 32 || !packed_weight || (!out_f32 && !out_split) || (n_out_cap && (!in_split || !nbr)))
     return P3D_ERR_INVALID_ARG;
   if (n_out_cap == 0) return P3D_OK;
   if ((reinterpret_cast<uintptr_t>(in_split) & 15) || (reinterpret_cast<uintptr_t>(out_f32) & 15) ||
       (reinterpret_cast<uintptr_t>(out_split) & 15) || (reinterpret_cast<uintptr_t>(packed_weight) & 15) ||
-      (reinterpret_cast<uintptr_t>(residual_split) & 15))
+      (reinterpret_cast<uintptr_t>(residual_split) & 15) || (reinterpret_cast<uintptr_t>(workspace) & 15))
     return P3D_ERR_INVALID_ARG;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-#define P3D_TC2_CASE(CI, CO)                                                                                        \
-  if (Cin == CI && Cout == CO)                                                                                      \
-    return tc2::launch<CI, CO>(in_split, nbr, n_out_dev, n_out_cap, K, packed_weight, scale, shift, residual_split, \
-                               relu, out_f32, out_split, st);
+  // split-K over taps for the layers with few 128-row tiles (same policy and scratch size as the fp32-row kernel)
+  int splits = tc::splits_for(Cout);
+  if (splits > K) splits = K;
+  const size_t need = static_cast<size_t>(splits) * static_cast<size_t>(n_out_cap) * Cout * sizeof(float);
+  const bool split = splits > 1 && workspace && workspace_bytes >= need;
+  float *k_f32 = split ? static_cast<float *>(workspace) : out_f32, *k_split = split ? nullptr : out_split;
+  const float *k_scale = split ? nullptr : scale, *k_shift = split ? nullptr : shift;
+  const float *k_res = split ? nullptr : residual_split;
+  const int k_relu = split ? 0 : relu, k_splits = split ? splits : 1;
+  int rc = P3D_ERR_UNSUPPORTED;
+#define P3D_TC2_CASE(CI, CO)                                                                                           \
+  if (Cin == CI && Cout == CO)                                                                                         \
+    rc = tc2::launch<CI, CO>(in_split, nbr, n_out_dev, n_out_cap, K, packed_weight, k_scale, k_shift, k_res, k_relu,    \
+                             k_f32, k_split, st, nullptr, k_splits);
   P3D_TC2_CASE(16, 16)
   P3D_TC2_CASE(16, 32)
   P3D_TC2_CASE(32, 32)
@@ -418,7 +549,21 @@ extern "C" int p3d_sparse_conv_gather_gemm_split(const float *in_split, const in
   P3D_TC2_CASE(64, 128)
   P3D_TC2_CASE(128, 128)
 #undef P3D_TC2_CASE
-  return P3D_ERR_UNSUPPORTED;
+  if (rc != P3D_OK || !split) return rc;
+  const long long fin_blocks = (n_out_cap * (Cout / 4) + 255) / 256;
+  tc2::rows_finalize_split_kernel<<<static_cast<unsigned int>(fin_blocks < kNumSMs * 8 ? fin_blocks : kNumSMs * 8), 256,
+                                    0, st>>>(k_f32, splits, n_out_dev, n_out_cap, Cout, scale, shift, residual_split,
+                                             relu, out_f32, out_split);
+  P3D_LAUNCH_CHECK();
+  return P3D_OK;
+}
+
+extern "C" int p3d_sparse_conv_gather_gemm_split(const float *in_split, const int32_t *nbr, const int32_t *n_out_dev,
+                                                 int64_t n_out_cap, int K, int Cin, int Cout, const float *packed_weight,
+                                                 const float *scale, const float *shift, const float *residual_split,
+                                                 int relu, float *out_f32, float *out_split, p3d_stream_t stream) {
+  return p3d_sparse_conv_gather_gemm_split_ws(in_split, nbr, n_out_dev, n_out_cap, K, Cin, Cout, packed_weight, scale,
+                                              shift, residual_split, relu, out_f32, out_split, nullptr, 0, stream);
 }
 
 // Debug aid (not part of the public header): same launch as p3d_sparse_conv_gather_gemm_split for the 64 -> 64

@@ -167,10 +167,12 @@ def _run(p, t, want):
         out_split = torch.empty((p.cap, 2 * p.cout), dtype=torch.float32, device=dev) if want == ROWS_SPLIT else None
         if PROFILE is not None:
             s_ev.record(st)
-        check(L.p3d_sparse_conv_gather_gemm_split(ptr(xin), ptr(p.nbr), ptr(p.num), p.cap, p.K, p.cin, p.cout,
-                                                  ptr(p.weight), ptr(p.scale), ptr(p.shift), ptr(res), int(p.relu),
-                                                  ptr(out_f32), ptr(out_split), stream(dev)),
-              "sparse_conv_gather_gemm_split")
+        wsb = L.p3d_sparse_conv_splitk_workspace_bytes(p.cap, p.cin, p.cout)  # > 0 for the wide (split-K) layers
+        ws = workspace(wsb, dev, "splitk") if wsb else None
+        check(L.p3d_sparse_conv_gather_gemm_split_ws(ptr(xin), ptr(p.nbr), ptr(p.num), p.cap, p.K, p.cin, p.cout,
+                                                     ptr(p.weight), ptr(p.scale), ptr(p.shift), ptr(res), int(p.relu),
+                                                     ptr(out_f32), ptr(out_split), ptr(ws), wsb, stream(dev)),
+              "sparse_conv_gather_gemm_split_ws")
         t._vals[ROWS_F32], t._vals[ROWS_SPLIT] = out_f32, out_split
     else:
         xin = p.x.get(ROWS_F32)
