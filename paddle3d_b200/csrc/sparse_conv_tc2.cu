@@ -1,19 +1,22 @@
-// Sparse-conv gather-GEMM on tcgen05, version 2: activations travel between layers already split into their
+// Sparse-conv gather-GEMM on tcgen05, split-row version: activations travel between layers already split into their
 // tf32 hi / lo halves (row layout [n][2][C]: hi row, then lo row), so the 3xTF32 split is paid ONCE per produced
 // element (in the producing layer's epilogue) instead of once per gathering neighbour (11-27x), and the gather
-// becomes a pure copy that cp.async (LDGSTS, 16 B, zero-fill for missing neighbours) drops straight into the
-// canonical UMMA core-matrix tiles — no register staging, no ALU in the producer loop, many stages in flight.
+// becomes a pure copy that cp.async (LDGSTS, 16 B, zero-fill for missing neighbours) drops straight into swizzled
+// UMMA operand tiles — no register staging, no ALU on the data in the producer loop.
 //
-//   grid      persistent: min(#tiles at capacity, 2 x SMs) CTAs, each walks tiles blockIdx.x, +gridDim.x, ...
-//             of the DEVICE row count (no empty CTAs for capacity-sized launches).
-//   warps 0-3 producers: per (tap, 16-channel chunk) use, 8 cp.async per thread (4 row groups x {hi, lo}); a warp
-//             instruction covers 8 rows x 64 contiguous bytes and lands on 512 contiguous bytes of shared memory
-//             (A tile: LBO = 128 B between k-chunks, SBO = 512 B between 8-row groups).  Completion is signalled
-//             with cp.async.mbarrier.arrive.noinc; producers run up to SA uses ahead.
-//   warp 5    weight TMA: cp.async.bulk of the packed [hi | lo] slice per use through its own, deeper ring.
-//   warp 4    MMA issuer: 3 tcgen05.mma.kind::tf32 per 8-wide k-step, tcgen05.commit back to both rings.
-//   warps 0-3 epilogue: tcgen05.ld, BN scale/shift (+bias), residual (= hi + lo of the split residual rows),
-//             ReLU, then either plain fp32 rows, split rows for the next layer, or both.
+//   grid        persistent: min(#work items at capacity, MIN_CTAS x SMs) CTAs, each walks the work items
+//               w = blockIdx.x, +gridDim.x, ... (w = tile * splits + split) of the DEVICE row count.
+//   warps 0..NPW-1  producers: per (tap, KC-channel chunk) "use", full-128-byte-line cp.async gathers (8 lanes per
+//               line, 4 rows per warp instruction) into SWIZZLE_128B (KC = 32) or SWIZZLE_64B (KC = 16) tiles;
+//               completion is signalled with cp.async.mbarrier.arrive.noinc.  Afterwards the same warps run the
+//               epilogue: tcgen05.ld, BN scale/shift (+bias), residual (= hi + lo of the split residual rows),
+//               ReLU, then plain fp32 rows, split rows for the next layer, or both.
+//   warp NPW    MMA issuer: 2 tcgen05.mma.kind::tf32 per 8-wide k-step, tcgen05.commit frees the stage.
+//   warp NPW+1  weight TMA: cp.async.bulk of the packed [hi | lo] slice of the use into the same stage.
+// The producer and MMA warps are bound by their own instruction latency (measured with tools/split_probe.py: the bare
+// barrier skeleton costs 550-690 cycles per use with 4 producer warps), so the row gather is spread over 8 warps
+// (or 4 CTAs per SM for the narrow layers) and the stage index restarts at 0 for every work item, which keeps the
+// operand addresses on the uniform datapath.
 #include "tc_common.cuh"
 
 namespace p3d {
@@ -23,20 +26,22 @@ using namespace tc;
 
 template <int CIN, int COUT>
 struct Cfg {
-  // One pipeline "use" = one tap x KC input channels for the CTA's 128 rows.  Every use costs ~800 cycles of
-  // fixed skeleton time in the single MMA-issuing warp (barrier wait, fences, commit — measured in-kernel with
-  // gathers, weight copies and MMAs all disabled), so uses are made as large as shared memory allows.
+  // One pipeline "use" = one tap x KC input channels for the CTA's 128 rows.
   static constexpr int KC = (CIN >= 32) ? 32 : 16;        // 32 channels = one full 128-byte line per gathered row half
   static constexpr int G = CIN / KC;
-  static constexpr int CH = KC / 4;                      // 16-byte k-chunks per use
   static constexpr int A_TILE = KC * kM * 4;             // one of hi / lo
   static constexpr int A_STAGE = 2 * A_TILE;
   static constexpr int B_STAGE = 2 * KC * COUT * 4;      // [chunk][hi rows | lo rows][16 B]
   static constexpr int STAGE = A_STAGE + B_STAGE;        // ONE ring: rows and weights of a use share a slot
-  static constexpr int BUDGET = (COUT <= 64) ? 100 * 1024 : 192 * 1024;   // two CTAs per SM except for Cout = 128
+  static constexpr bool NARROW = (CIN == 16 && COUT <= 32);
+  static constexpr int MIN_CTAS = NARROW ? 4 : (COUT <= 64 ? 2 : 1);
+  static constexpr int NPW = NARROW ? 4 : 8;             // producer (= epilogue) warps
+  static constexpr int THREADS = NPW * 32 + 64;
+  static constexpr int RPW = kM / NPW;                   // rows gathered by one producer warp
+  static constexpr int QN = RPW / 4;                     // warp instructions (4 rows each) per use and row half
+  static constexpr int BUDGET = NARROW ? 40 * 1024 : (COUT <= 64 ? 100 * 1024 : 192 * 1024);
   static constexpr int S_RAW = BUDGET / STAGE;
   static constexpr int STAGES = S_RAW > 8 ? 8 : (S_RAW < 2 ? 2 : S_RAW);
-  static constexpr int MIN_CTAS = (COUT <= 64) ? 2 : 1;
   // Two MMAs per 8-wide k-step: [B_hi | B_lo] is one K-major operand of 2*Cout rows, so
   //   acc[0 .. 2N)   += A_hi x [B_hi | B_lo]      (N' = 2*Cout)
   //   acc[2N .. 3N)  += A_lo x B_hi               (N  = Cout)
@@ -49,10 +54,12 @@ struct Cfg {
                                     (static_cast<uint32_t>(kM >> 4) << 24);
   static_assert(CIN % 16 == 0 && COUT % 16 == 0 && COUT <= 128, "tensor-core path needs 16-channel multiples");
   static_assert(MIN_CTAS * TMEM_COLS <= 512, "TMEM over-subscribed");
+  static_assert(STAGE % 1024 == 0 || KC == 16, "SWIZZLE_128B tiles need 1024-byte alignment");
+  static_assert(STAGE % 512 == 0, "SWIZZLE_64B tiles need 512-byte alignment");
 };
 
 // debug only (p3d_debug_set_flags): 1 skip weight copies, 2 skip row gathers, 4 skip MMAs, 8 skip fence.proxy.async,
-// 16 plain mbarrier arrive instead of tcgen05.commit, 32 plain arrive instead of cp.async.mbarrier.arrive.noinc
+// 16 plain mbarrier arrive instead of tcgen05.commit
 __device__ int g_dbg_flags = 0;
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src, bool valid) {
@@ -85,8 +92,7 @@ __device__ __forceinline__ uint64_t smem_desc_sw64(uint32_t addr) {
   return d;
 }
 
-// Warp-uniform issue: every lane executes the instruction stream (so the descriptors stay in uniform registers
-// instead of going through a per-MMA R2UR waterfall), one elected lane issues.
+// Warp-uniform issue: every lane executes the instruction stream, one elected lane issues.
 __device__ __forceinline__ void umma_tf32_elect(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                                 uint32_t accumulate) {
   asm volatile(
@@ -106,16 +112,19 @@ __device__ __forceinline__ void umma_commit_elect(uint32_t bar) {
 }
 
 template <int CIN, int COUT>
-__global__ void __launch_bounds__(kThreads, Cfg<CIN, COUT>::MIN_CTAS)
+__global__ void __launch_bounds__(Cfg<CIN, COUT>::THREADS, Cfg<CIN, COUT>::MIN_CTAS)
     gather_gemm_split_kernel(const float *__restrict__ in_split, const int32_t *__restrict__ nbr,
                              const int32_t *__restrict__ n_out_dev, long long n_cap, int K, int splits,
                              const float *__restrict__ packed_w, const float *__restrict__ scale,
                              const float *__restrict__ shift, const float *__restrict__ residual_split, int relu,
                              float *__restrict__ out_f32, float *__restrict__ out_split, long long *__restrict__ dbg) {
-  // dbg (optional, CTA 0 only): per-use clock64 timeline, 8 slots per use:
+  // dbg (optional, CTA 0 only): per-use clock64 timeline, 8 slots per use (first 512 uses):
   //   0 producer(warp0): slot free   1 producer: cp.async issued   2 TMA: slot free   3 TMA: issued
   //   5 MMA: slot full               6 MMA: issued + committed
+  // and from dbg[4096], 4 slots per work item (first 64): item start, neighbour map in smem, accumulators complete,
+  // epilogue stored; dbg[4096 + 256 ..]: kernel entry, prologue done, exit.
   using C = Cfg<CIN, COUT>;
+  constexpr int kMmaWarp = C::NPW, kTmaWarp = C::NPW + 1;
   const long long n = n_out_dev ? min(static_cast<long long>(n_out_dev[0]), n_cap) : n_cap;
   // work items w = tile * splits + split; split s owns the taps t == s (mod splits) and, when splits > 1, writes raw
   // partial sums to slab s of out_f32 (the caller passes the scratch slabs and no epilogue operands).
@@ -125,21 +134,25 @@ __global__ void __launch_bounds__(kThreads, Cfg<CIN, COUT>::MIN_CTAS)
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   int32_t *s_nbr = reinterpret_cast<int32_t *>(smem + C::STAGES * C::STAGE);  // [kM][K]
-  __shared__ __align__(8) unsigned long long s_bar[8 + 8 + 1];  // full[8] empty[8] tmem_full
-  constexpr int kF = 0, kE = 8, kTF = 16;
+  __shared__ __align__(8) unsigned long long s_bar[8 + 8 + 2];  // full[8] empty[8] tmem_full nbr_loaded
+  constexpr int kF = 0, kE = 8, kTF = 16, kNB = 17;
   __shared__ uint32_t s_tmem_base;
   __shared__ uint32_t s_active;
 
   const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
-  if (tid == kProducers) {
+  const bool dbg0 = dbg && blockIdx.x == 0 && tid == 0;
+  if (dbg0) dbg[4096 + 256] = clock64();
+  if (tid == kMmaWarp * 32) {
     for (int s = 0; s < C::STAGES; ++s) {
-      mbar_init(smem_u32(&s_bar[kF + s]), kProducers + 1);  // 128 cp.async completions + the weight copy's expect_tx
-      mbar_init(smem_u32(&s_bar[kE + s]), 1);               // tcgen05.commit
+      mbar_init(smem_u32(&s_bar[kF + s]), C::NPW * 32 + 1);  // cp.async completions of every producer thread + the
+                                                             // weight copy's expect_tx arrival
+      mbar_init(smem_u32(&s_bar[kE + s]), 1);                // tcgen05.commit
     }
     mbar_init(smem_u32(&s_bar[kTF]), 1);
+    mbar_init(smem_u32(&s_bar[kNB]), 1);
     fence_mbar_init();
   }
-  if (wid == 4) {
+  if (wid == kMmaWarp) {
     __syncwarp();
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem_base)),
                  "r"(static_cast<uint32_t>(C::TMEM_COLS))
@@ -151,10 +164,14 @@ __global__ void __launch_bounds__(kThreads, Cfg<CIN, COUT>::MIN_CTAS)
   tc_fence_after();
   const uint32_t tmem_base = s_tmem_base;
   const uint32_t ring = smem_u32(smem);
+  if (dbg0) dbg[4096 + 257] = clock64();
 
-  int use_base = 0;  // pipeline uses consumed by earlier tiles of this CTA (ring phases keep running)
-  int tile_it = 0;
-  for (long long w = blockIdx.x; w < n_work; w += gridDim.x, ++tile_it) {
+  // Every role walks the stages 0, 1, .. of each work item in the same order and keeps the parity it expects next
+  // on each stage's barrier in a bit mask (bit s): the stage index depends on loop counters only.
+  uint32_t ph = (wid == kMmaWarp) ? 0u : 0xffffffffu;  // full-barrier waits start at parity 0, empty-barrier waits at 1
+  int use_base = 0;                                    // uses of earlier items (debug timeline index only)
+  int item_it = 0;
+  for (long long w = blockIdx.x; w < n_work; w += gridDim.x, ++item_it) {
     const long long tile = w / splits;
     const int split = static_cast<int>(w - tile * splits);
     float *out_rows = out_f32 ? out_f32 + static_cast<size_t>(split) * static_cast<size_t>(n_cap) * COUT : nullptr;
@@ -166,95 +183,98 @@ __global__ void __launch_bounds__(kThreads, Cfg<CIN, COUT>::MIN_CTAS)
     const long long row0 = tile * kM;
     const int rows = static_cast<int>(min(static_cast<long long>(kM), n - row0));
     if (tid == 0) s_active = 0u;
-    __syncthreads();  // previous tile fully drained (epilogue done, s_nbr free)
+    __syncthreads();  // previous item fully drained (epilogue done, s_nbr free)
+    if (dbg0 && item_it < 64) dbg[4096 + item_it * 4] = clock64();
     {
-      uint32_t mine = 0u;
-      for (int q = tid; q < kM * K; q += kThreads) {
-        const int v = (q < rows * K) ? __ldg(nbr + row0 * K + q) : -1;
-        s_nbr[q] = v;
-        if (v >= 0) mine |= 1u << (q % K);
+      // the tile's neighbour map is one contiguous block of the [n_cap, K] array: one bulk copy instead of a
+      // latency-bound load loop (measured ~10k cycles per work item); rows >= `rows` of the block are never used.
+      const int avail = static_cast<int>(min(static_cast<long long>(kM), n_cap - row0));
+      const uint32_t words = static_cast<uint32_t>(avail) * K, bulk_words = words & ~3u;
+      if (tid == 0) {
+        fence_proxy_async();  // earlier generic reads of s_nbr vs the async-proxy write
+        mbar_arrive_expect_tx(smem_u32(&s_bar[kNB]), bulk_words * 4);
+        if (bulk_words) bulk_g2s(smem_u32(s_nbr), nbr + row0 * K, bulk_words * 4, smem_u32(&s_bar[kNB]));
       }
+      if (bulk_words + tid < words) s_nbr[bulk_words + tid] = __ldg(nbr + row0 * K + bulk_words + tid);
+      if (bulk_words != words) __syncthreads();  // (uniform) the up-to-3 tail words are plain stores
+      mbar_wait(smem_u32(&s_bar[kNB]), static_cast<uint32_t>(item_it & 1));
+      uint32_t mine = 0u;
+      for (int q = tid; q < rows * K; q += C::THREADS)
+        if (s_nbr[q] >= 0) mine |= 1u << (q % K);
       mine = __reduce_or_sync(0xffffffffu, mine);
       if (lane == 0 && mine) atomicOr(&s_active, mine);
     }
     __syncthreads();
     const uint32_t active = s_active & tap_mask;
+    if (dbg0 && item_it < 64) dbg[4096 + item_it * 4 + 1] = clock64();
     const int n_uses = __popc(active) * C::G;
     const int flags = dbg ? g_dbg_flags : 0;  // only the debug entry point passes dbg
 
-    if (wid < 4) {
+    if (wid < C::NPW) {
       // ---------------------------------------------------------------- producers (cp.async gathers)
-      // a warp instruction covers 8 rows x 4 k-chunks: 64 contiguous bytes per gathered row, 512 contiguous bytes of
-      // shared memory (A tile: k-chunk stride LBO = 128 B inside a 4-chunk block, 8-row groups SBO = 512 B apart,
-      // 16-channel blocks 8 KB apart).
-      int use = use_base;
+      // FULL-LINE gathers (measured 36-72 B/clk/SM vs 11-19 for 64-byte pieces, tools/gather_microbench.cu): 8 lanes
+      // fetch one 128-byte line, a warp instruction covers 4 rows and lands on 512 (KC = 32) or 2 x 256 (KC = 16)
+      // contiguous bytes of the swizzled tiles: no bank conflicts.
+      const int sub = lane >> 3;
+      int s = 0, u = 0;
       for (int t = 0; t < K; ++t) {
         if (!((active >> t) & 1u)) continue;
-        if (C::KC == 32) {
-          // FULL-LINE gathers (measured 36-72 B/clk/SM vs 11-19 for 64-byte pieces, tools/gather_microbench.cu):
-          // 8 lanes fetch the 128 contiguous bytes (32 channels) of one row half, a warp instruction covers 4 rows;
-          // destination = SWIZZLE_128B tile (row pitch 128 B, chunk ^= row & 7): 512 contiguous bytes, no conflicts.
-          const int sub = lane >> 3, ch = lane & 7;
-          int src[8];
+        int src[C::QN];
 #pragma unroll
-          for (int q = 0; q < 8; ++q) src[q] = s_nbr[(wid * 32 + q * 4 + sub) * K + t];
-          for (int g = 0; g < C::G; ++g, ++use) {
-            const int s = use % C::STAGES;
-            mbar_wait(smem_u32(&s_bar[kE + s]), (static_cast<uint32_t>(use / C::STAGES) & 1u) ^ 1u);
-            if (dbg && blockIdx.x == 0 && tid == 0 && use < 512) dbg[use * 8 + 0] = clock64();
-            const uint32_t st = ring + static_cast<uint32_t>(s * C::STAGE);
+        for (int q = 0; q < C::QN; ++q) {
+          const int row = wid * C::RPW + q * 4 + sub;
+          src[q] = row < rows ? s_nbr[row * K + t] : -1;
+        }
+        for (int g = 0; g < C::G; ++g, ++u) {
+          mbar_wait(smem_u32(&s_bar[kE + s]), (ph >> s) & 1u);
+          ph ^= 1u << s;
+          if (dbg0 && use_base + u < 512) dbg[(use_base + u) * 8 + 0] = clock64();
+          const uint32_t st = ring + static_cast<uint32_t>(s * C::STAGE);
+          if (C::KC == 32) {
+            // SWIZZLE_128B tiles (row pitch 128 B, chunk ^= row & 7); the hi and the lo line of a row
+            const int ch = lane & 7;
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
+            for (int q = 0; q < C::QN; ++q) {
               const bool ok = src[q] >= 0;
-              const int row = wid * 32 + q * 4 + sub;
+              const int row = wid * C::RPW + q * 4 + sub;
               const float *p = in_split + (ok ? static_cast<size_t>(src[q]) * (2 * CIN) : 0) + g * 32 + ch * 4;
               const uint32_t d = st + static_cast<uint32_t>(row * 128 + ((ch ^ (row & 7)) << 4));
               if (flags & 2) continue;
-              cp_async16(d, p, ok);                       // hi
-              cp_async16(d + C::A_TILE, p + CIN, ok);     // lo
+              cp_async16(d, p, ok);                    // hi
+              cp_async16(d + C::A_TILE, p + CIN, ok);  // lo
             }
-            if (flags & 32)
-              mbar_arrive(smem_u32(&s_bar[kF + s]));
-            else
-              cp_async_arrive_noinc(smem_u32(&s_bar[kF + s]));
-            if (dbg && blockIdx.x == 0 && tid == 0 && use < 512) dbg[use * 8 + 1] = clock64();
-          }
-        } else {
-          // 16-channel layers: a split row [hi 16 | lo 16] is ONE 128-byte line: 8 lanes fetch it (lanes 0-3 the hi
-          // chunks, 4-7 the lo chunks), a warp instruction covers 4 rows; tiles are SWIZZLE_64B (row pitch 64 B).
-          const int sub = lane >> 3, ch = lane & 3, part = (lane >> 2) & 1;
-          int src[8];
+          } else {
+            // 16-channel layers: a split row [hi 16 | lo 16] is ONE line (lanes 0-3 of a row fetch the hi chunks,
+            // 4-7 the lo chunks); SWIZZLE_64B tiles (row pitch 64 B, chunk ^= (row >> 1) & 3)
+            const int ch = lane & 3, part = (lane >> 2) & 1;
 #pragma unroll
-          for (int q = 0; q < 8; ++q) src[q] = s_nbr[(wid * 32 + q * 4 + sub) * K + t];
-          for (int g = 0; g < C::G; ++g, ++use) {
-            const int s = use % C::STAGES;
-            mbar_wait(smem_u32(&s_bar[kE + s]), (static_cast<uint32_t>(use / C::STAGES) & 1u) ^ 1u);
-            const uint32_t st = ring + static_cast<uint32_t>(s * C::STAGE);
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
+            for (int q = 0; q < C::QN; ++q) {
               const bool ok = src[q] >= 0;
-              const int row = wid * 32 + q * 4 + sub;
+              const int row = wid * C::RPW + q * 4 + sub;
               const float *p = in_split + (ok ? static_cast<size_t>(src[q]) * (2 * CIN) : 0) + part * CIN + g * 16 + ch * 4;
               const uint32_t d = st + static_cast<uint32_t>(part * C::A_TILE + row * 64 + ((ch ^ ((row >> 1) & 3)) << 4));
               if (flags & 2) continue;
               cp_async16(d, p, ok);
             }
-            if (flags & 32)
-              mbar_arrive(smem_u32(&s_bar[kF + s]));
-            else
-              cp_async_arrive_noinc(smem_u32(&s_bar[kF + s]));
           }
+          cp_async_arrive_noinc(smem_u32(&s_bar[kF + s]));
+          if (dbg0 && use_base + u < 512) dbg[(use_base + u) * 8 + 1] = clock64();
+          s = (s + 1 == C::STAGES) ? 0 : s + 1;
         }
       }
       // ---------------------------------------------------------------- epilogue
-      mbar_wait(smem_u32(&s_bar[kTF]), static_cast<uint32_t>(tile_it & 1));
+      mbar_wait(smem_u32(&s_bar[kTF]), static_cast<uint32_t>(item_it & 1));
       tc_fence_after();
-      const int r = tid;
-      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(wid * 32) << 16);
+      if (dbg0 && item_it < 64) dbg[4096 + item_it * 4 + 2] = clock64();
+      // warp w reads TMEM lanes 32 * (w & 3) ..; with 8 epilogue warps the two warps of a lane quarter take
+      // alternate 16-column chunks
+      const int quarter = wid & 3;
+      const int r = quarter * 32 + lane;
+      const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
       const bool live = r < rows;
       const size_t orow = static_cast<size_t>(row0 + r);
 #pragma unroll 1
-      for (int c0 = 0; c0 < COUT; c0 += 16) {
+      for (int c0 = (wid >> 2) * 16; c0 < COUT; c0 += 16 * (C::NPW / 4)) {
         uint32_t a[16];
         if (n_uses > 0) {
           asm volatile(
@@ -322,16 +342,17 @@ __global__ void __launch_bounds__(kThreads, Cfg<CIN, COUT>::MIN_CTAS)
         }
       }
       tc_fence_before();
-    } else if (wid == 4) {
+      if (dbg0 && item_it < 64) dbg[4096 + item_it * 4 + 3] = clock64();
+    } else if (wid == kMmaWarp) {
       // ---------------------------------------------------------------- MMA issuer (whole warp runs the stream)
       if (n_uses == 0) {
         if (lane == 0) mbar_arrive(smem_u32(&s_bar[kTF]));
       } else {
+        int s = 0;
         for (int u = 0; u < n_uses; ++u) {
-          const int use = use_base + u;
-          const int s = use % C::STAGES;
-          mbar_wait(smem_u32(&s_bar[kF + s]), static_cast<uint32_t>(use / C::STAGES) & 1u);
-          if (dbg && blockIdx.x == 0 && lane == 0 && use < 512) dbg[use * 8 + 5] = clock64();
+          mbar_wait(smem_u32(&s_bar[kF + s]), (ph >> s) & 1u);
+          ph ^= 1u << s;
+          if (dbg && blockIdx.x == 0 && lane == 0 && use_base + u < 512) dbg[(use_base + u) * 8 + 5] = clock64();
           if (!(flags & 8)) fence_proxy_async();  // cp.async (generic proxy) writes -> tensor-core (async proxy) reads
           tc_fence_after();
           const uint32_t a_hi = ring + static_cast<uint32_t>(s * C::STAGE), a_lo = a_hi + C::A_TILE;
@@ -364,20 +385,21 @@ __global__ void __launch_bounds__(kThreads, Cfg<CIN, COUT>::MIN_CTAS)
             umma_commit_elect(smem_u32(&s_bar[kE + s]));
             if (u == n_uses - 1) umma_commit_elect(smem_u32(&s_bar[kTF]));
           }
-          if (dbg && blockIdx.x == 0 && lane == 0 && use < 512) dbg[use * 8 + 6] = clock64();
+          if (dbg && blockIdx.x == 0 && lane == 0 && use_base + u < 512) dbg[(use_base + u) * 8 + 6] = clock64();
+          s = (s + 1 == C::STAGES) ? 0 : s + 1;
         }
       }
       tc_fence_before();
     } else {
       // ---------------------------------------------------------------- weight TMA (one lane)
       if (lane == 0) {
-        int use = use_base;
+        int s = 0, u = 0;
         for (int t = 0; t < K; ++t) {
           if (!((active >> t) & 1u)) continue;
-          for (int g = 0; g < C::G; ++g, ++use) {
-            const int s = use % C::STAGES;
-            mbar_wait(smem_u32(&s_bar[kE + s]), (static_cast<uint32_t>(use / C::STAGES) & 1u) ^ 1u);
-            if (dbg && blockIdx.x == 0 && use < 512) dbg[use * 8 + 2] = clock64();
+          for (int g = 0; g < C::G; ++g, ++u) {
+            mbar_wait(smem_u32(&s_bar[kE + s]), (ph >> s) & 1u);
+            ph ^= 1u << s;
+            if (dbg && blockIdx.x == 0 && use_base + u < 512) dbg[(use_base + u) * 8 + 2] = clock64();
             if (flags & 1) {
               mbar_arrive(smem_u32(&s_bar[kF + s]));
             } else {
@@ -386,7 +408,8 @@ __global__ void __launch_bounds__(kThreads, Cfg<CIN, COUT>::MIN_CTAS)
                        packed_w + (static_cast<size_t>(t) * CIN + g * C::KC) * (2 * COUT), static_cast<uint32_t>(C::B_STAGE),
                        smem_u32(&s_bar[kF + s]));
             }
-            if (dbg && blockIdx.x == 0 && use < 512) dbg[use * 8 + 3] = clock64();
+            if (dbg && blockIdx.x == 0 && use_base + u < 512) dbg[(use_base + u) * 8 + 3] = clock64();
+            s = (s + 1 == C::STAGES) ? 0 : s + 1;
           }
         }
       }
@@ -395,7 +418,8 @@ __global__ void __launch_bounds__(kThreads, Cfg<CIN, COUT>::MIN_CTAS)
   }
   tc_fence_before();
   __syncthreads();
-  if (wid == 4) {
+  if (dbg0) dbg[4096 + 258] = clock64();
+  if (wid == kMmaWarp) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
                  "r"(static_cast<uint32_t>(C::TMEM_COLS))
@@ -415,8 +439,8 @@ int launch(const float *in_split, const int32_t *nbr, const int32_t *n_out_dev, 
   const long long work = ((n_cap + kM - 1) / kM) * splits;
   const long long slots = static_cast<long long>(kNumSMs) * C::MIN_CTAS;
   const unsigned int grid = static_cast<unsigned int>(work < slots ? work : slots);
-  kern<<<grid, kThreads, smem, st>>>(in_split, nbr, n_out_dev, n_cap, K, splits, packed, scale, shift, residual_split, relu,
-                                     out_f32, out_split, dbg);
+  kern<<<grid, C::THREADS, smem, st>>>(in_split, nbr, n_out_dev, n_cap, K, splits, packed, scale, shift, residual_split,
+                                       relu, out_f32, out_split, dbg);
   P3D_LAUNCH_CHECK();
   return P3D_OK;
 }
@@ -524,7 +548,8 @@ extern "C" int p3d_sparse_conv_gather_gemm_split_ws(const float *in_split, const
   if (n_out_cap == 0) return P3D_OK;
   if ((reinterpret_cast<uintptr_t>(in_split) & 15) || (reinterpret_cast<uintptr_t>(out_f32) & 15) ||
       (reinterpret_cast<uintptr_t>(out_split) & 15) || (reinterpret_cast<uintptr_t>(packed_weight) & 15) ||
-      (reinterpret_cast<uintptr_t>(residual_split) & 15) || (reinterpret_cast<uintptr_t>(workspace) & 15))
+      (reinterpret_cast<uintptr_t>(residual_split) & 15) || (reinterpret_cast<uintptr_t>(workspace) & 15) ||
+      (reinterpret_cast<uintptr_t>(nbr) & 15))
     return P3D_ERR_INVALID_ARG;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   // split-K over taps for the layers with few 128-row tiles (same policy and scratch size as the fp32-row kernel)
@@ -566,13 +591,25 @@ extern "C" int p3d_sparse_conv_gather_gemm_split(const float *in_split, const in
                                               shift, residual_split, relu, out_f32, out_split, nullptr, 0, stream);
 }
 
-// Debug aid (not part of the public header): same launch as p3d_sparse_conv_gather_gemm_split for the 64 -> 64
-// configuration with a per-use clock64 timeline of CTA 0 written to dbg[512 * 8].
-extern "C" int p3d_debug_split_timeline_64(const float *in_split, const int32_t *nbr, const int32_t *n_out_dev,
-                                           int64_t n_out_cap, int K, const float *packed_weight, float *out_f32,
-                                           long long *dbg, p3d_stream_t stream) {
-  return tc2::launch<64, 64>(in_split, nbr, n_out_dev, n_out_cap, K, packed_weight, nullptr, nullptr, nullptr, 0, out_f32,
-                             nullptr, static_cast<cudaStream_t>(stream), dbg);
+// Debug aid (not part of the public header): the launch of p3d_sparse_conv_gather_gemm_split with a clock64 timeline of
+// CTA 0 written to dbg[4096 + 260] (layout in the kernel's header comment); tools/split_probe.py reads it.
+extern "C" int p3d_debug_split_launch(const float *in_split, const int32_t *nbr, const int32_t *n_out_dev,
+                                      int64_t n_out_cap, int K, int Cin, int Cout, const float *packed_weight,
+                                      float *out_f32, long long *dbg, int splits, p3d_stream_t stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+#define P3D_TC2_CASE(CI, CO)                                                                                          \
+  if (Cin == CI && Cout == CO)                                                                                        \
+    return tc2::launch<CI, CO>(in_split, nbr, n_out_dev, n_out_cap, K, packed_weight, nullptr, nullptr, nullptr, 0,   \
+                               out_f32, nullptr, st, dbg, splits);
+  P3D_TC2_CASE(16, 16)
+  P3D_TC2_CASE(16, 32)
+  P3D_TC2_CASE(32, 32)
+  P3D_TC2_CASE(32, 64)
+  P3D_TC2_CASE(64, 64)
+  P3D_TC2_CASE(64, 128)
+  P3D_TC2_CASE(128, 128)
+#undef P3D_TC2_CASE
+  return P3D_ERR_UNSUPPORTED;
 }
 
 extern "C" int p3d_debug_set_flags(int flags) {
