@@ -182,7 +182,7 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--precision", default="tf32x3", choices=["fp32", "tf32x3", "tf32x3_split"])
+    ap.add_argument("--precision", default="tf32x3_split", choices=["fp32", "tf32x3", "tf32x3_split"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -298,6 +298,7 @@ def main():
                 x.values()
                 ev[2].record(st)
                 x.to_dense_bev()
+                pipe.net.join()
                 ev[3].record(st)
                 h, tc = pipe.head, pipe.test_cfg
                 cpp.centerpoint_postprocess_device(h["hm"], h["reg"], h["height"], h["dim"], h["vel"], h["rot"],
@@ -337,7 +338,7 @@ def main():
                     "algorithmic_bytes": vox_bytes, "ms": ms_vox, "peak_source": peak_src}
         if tc_ms > 0:
             ach = tc_flops / (tc_ms * 1e-3) / 1e12
-            roof = {"bound": "tensor", "kernel": "tc::gather_gemm_tf32x3_kernel (all tensor-core sparse convs of one frame)",
+            roof = {"bound": "tensor", "kernel": ("tc2::gather_gemm_split_kernel" if precision == sp.TF32X3_SPLIT else "tc::gather_gemm_tf32x3_kernel") + " (all tensor-core sparse convs of one frame)",
                     "achieved": ach, "peak": bf16_peak, "unit": "TFLOP/s", "frac": ach / bf16_peak, "traffic": None,
                     "algorithmic_flops": tc_flops, "ms": tc_ms,
                     "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst)" if pk else "fallback 1.59 PFLOP/s",

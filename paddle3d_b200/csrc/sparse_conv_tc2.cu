@@ -125,6 +125,11 @@ __global__ void __launch_bounds__(Cfg<CIN, COUT>::THREADS, Cfg<CIN, COUT>::MIN_C
   // epilogue stored; dbg[4096 + 256 ..]: kernel entry, prologue done, exit.
   using C = Cfg<CIN, COUT>;
   constexpr int kMmaWarp = C::NPW, kTmaWarp = C::NPW + 1;
+  // Programmatic dependent launch: let the next kernel of the stream start its prologue while this grid drains, and
+  // (below) do this kernel's own prologue - barriers, TMEM, neighbour map - before waiting for the previous grid.
+  // Nothing read before griddepcontrol.wait is written by the preceding conv layer (row count, neighbour map and
+  // packed weights come from the rulebook / init kernels, which never signal early).
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const long long n = n_out_dev ? min(static_cast<long long>(n_out_dev[0]), n_cap) : n_cap;
   // work items w = tile * splits + split; split s owns the taps t == s (mod splits) and, when splits > 1, writes raw
   // partial sums to slab s of out_f32 (the caller passes the scratch slabs and no epilogue operands).
@@ -206,6 +211,7 @@ __global__ void __launch_bounds__(Cfg<CIN, COUT>::THREADS, Cfg<CIN, COUT>::MIN_C
     }
     __syncthreads();
     const uint32_t active = s_active & tap_mask;
+    if (item_it == 0) asm volatile("griddepcontrol.wait;" ::: "memory");  // inputs of the previous layer are complete
     if (dbg0 && item_it < 64) dbg[4096 + item_it * 4 + 1] = clock64();
     const int n_uses = __popc(active) * C::G;
     const int flags = dbg ? g_dbg_flags : 0;  // only the debug entry point passes dbg
@@ -345,11 +351,14 @@ __global__ void __launch_bounds__(Cfg<CIN, COUT>::THREADS, Cfg<CIN, COUT>::MIN_C
       if (dbg0 && item_it < 64) dbg[4096 + item_it * 4 + 3] = clock64();
     } else if (wid == kMmaWarp) {
       // ---------------------------------------------------------------- MMA issuer (whole warp runs the stream)
-      if (n_uses == 0) {
+      // the warp-reduction result lives in a uniform register: trip count, stage index and with them the operand
+      // descriptors stay on the uniform datapath (no per-MMA R2UR of descriptor words)
+      const int n_uses_u = __popc(__reduce_or_sync(0xffffffffu, active)) * C::G;
+      if (n_uses_u == 0) {
         if (lane == 0) mbar_arrive(smem_u32(&s_bar[kTF]));
       } else {
         int s = 0;
-        for (int u = 0; u < n_uses; ++u) {
+        for (int u = 0; u < n_uses_u; ++u) {
           mbar_wait(smem_u32(&s_bar[kF + s]), (ph >> s) & 1u);
           ph ^= 1u << s;
           if (dbg && blockIdx.x == 0 && lane == 0 && use_base + u < 512) dbg[(use_base + u) * 8 + 5] = clock64();
@@ -378,12 +387,12 @@ __global__ void __launch_bounds__(Cfg<CIN, COUT>::THREADS, Cfg<CIN, COUT>::MIN_C
           if (flags & 16) {
             if (lane == 0) {
               mbar_arrive(smem_u32(&s_bar[kE + s]));
-              if (u == n_uses - 1) mbar_arrive(smem_u32(&s_bar[kTF]));
+              if (u == n_uses_u - 1) mbar_arrive(smem_u32(&s_bar[kTF]));
             }
             __syncwarp();
           } else {
             umma_commit_elect(smem_u32(&s_bar[kE + s]));
-            if (u == n_uses - 1) umma_commit_elect(smem_u32(&s_bar[kTF]));
+            if (u == n_uses_u - 1) umma_commit_elect(smem_u32(&s_bar[kTF]));
           }
           if (dbg && blockIdx.x == 0 && lane == 0 && use_base + u < 512) dbg[(use_base + u) * 8 + 6] = clock64();
           s = (s + 1 == C::STAGES) ? 0 : s + 1;
@@ -439,8 +448,20 @@ int launch(const float *in_split, const int32_t *nbr, const int32_t *n_out_dev, 
   const long long work = ((n_cap + kM - 1) / kM) * splits;
   const long long slots = static_cast<long long>(kNumSMs) * C::MIN_CTAS;
   const unsigned int grid = static_cast<unsigned int>(work < slots ? work : slots);
-  kern<<<grid, C::THREADS, smem, st>>>(in_split, nbr, n_out_dev, n_cap, K, splits, packed, scale, shift, residual_split,
-                                       relu, out_f32, out_split, dbg);
+  static const bool pdl = !(getenv("P3D_PDL") && atoi(getenv("P3D_PDL")) == 0);  // tuning hook, default on
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(C::THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  const long long n_cap_ll = n_cap;
+  P3D_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, in_split, nbr, n_out_dev, n_cap_ll, K, splits, packed, scale, shift,
+                                    residual_split, relu, out_f32, out_split, dbg));
   P3D_LAUNCH_CHECK();
   return P3D_OK;
 }

@@ -88,7 +88,7 @@ __device__ __forceinline__ void split_tf32(float x, float &hi, float &lo) {
 // split-K factor of the tensor-core sparse conv (taps spread over this many CTAs per 128-row tile)
 inline int splits_for(int Cout) {
   // tuning hooks (not a public knob): P3D_SPLITS_128 / P3D_SPLITS_64 / P3D_SPLITS_32 override the defaults
-  static const int s128 = getenv("P3D_SPLITS_128") ? atoi(getenv("P3D_SPLITS_128")) : 3;
+  static const int s128 = getenv("P3D_SPLITS_128") ? atoi(getenv("P3D_SPLITS_128")) : 2;
   static const int s64 = getenv("P3D_SPLITS_64") ? atoi(getenv("P3D_SPLITS_64")) : 2;
   static const int s32 = getenv("P3D_SPLITS_32") ? atoi(getenv("P3D_SPLITS_32")) : 1;
   const int v = Cout >= 128 ? s128 : (Cout >= 64 ? s64 : s32);

@@ -50,6 +50,8 @@ class _IndexSet:
     def __init__(self, coords, num, cap, batch, spatial, table=None):
         self.coords, self.num, self.cap, self.batch, self.spatial = coords, num, cap, batch, list(spatial)
         self.subm_rulebooks = {}
+        self.strided = {}      # id(Conv3D layer) -> (output _IndexSet, neighbour map), see _ConvBase.build_index
+        self.ready = {}        # rulebook key -> _Ready: built on another stream (prepare pass), wait before first use
         self._table = table
 
     def table(self):
@@ -74,6 +76,20 @@ class _IndexSet:
                                                    ptr(nbr), stream(dev)), "sparse_rulebook_subm_t")
             self.subm_rulebooks[k] = nbr
         return nbr
+
+
+class _Ready:
+    """Event recorded on the stream that built a rulebook; the consuming stream waits for it once."""
+
+    def __init__(self, stream_):
+        self.event = torch.cuda.Event()
+        self.event.record(stream_)
+        self.waited = False
+
+    def wait(self, stream_):
+        if not self.waited:
+            stream_.wait_event(self.event)
+            self.waited = True
 
 
 class SparseCooTensor:
@@ -145,8 +161,33 @@ def sparse_coo_tensor(indices, values, shape, stop_gradient=True, num=None):
     return SparseCooTensor(idx, values=values, channels=int(shape[4]))
 
 
+def prepare_rulebooks(index, conv_layers, side_stream):
+    """Build the index sets and neighbour maps of `conv_layers` (SubmConv3D / Conv3D, execution order, starting at
+    `index`) on `side_stream`: they depend on coordinates only, so they can run beside the first feature layers. Every
+    rulebook gets a _Ready event that the consuming launch waits for."""
+    dev = index.coords.device
+    main = torch.cuda.current_stream(dev)
+    side_stream.wait_stream(main)
+    with torch.cuda.stream(side_stream):
+        for l in conv_layers:
+            if l.subm:
+                k = (l.key if l.key is not None else "_anon", tuple(l.kernel_size))
+                key = ("subm",) + k
+                if key not in index.ready and k not in index.subm_rulebooks:
+                    index.subm_rulebook(l.kernel_size, l.key)
+                    index.ready[key] = _Ready(side_stream)
+            else:
+                key = ("conv", id(l))
+                fresh = id(l) not in index.strided
+                nxt, _ = l.build_index(index)
+                if fresh:
+                    index.ready[key] = _Ready(side_stream)
+                index = nxt
+
+
 class _Pending:
-    __slots__ = ("x", "nbr", "num", "cap", "K", "cin", "cout", "weight", "scale", "shift", "residual", "relu", "precision")
+    __slots__ = ("x", "nbr", "num", "cap", "K", "cin", "cout", "weight", "scale", "shift", "residual", "relu", "precision",
+                 "ready")
 
 
 PROFILE = None  # set to a list to record (cin, cout, K, precision, nbr, num, start_event, end_event) per conv launch
@@ -158,6 +199,8 @@ def _run(p, t, want):
     L = lib()
     dev = p.nbr.device
     st = torch.cuda.current_stream(dev)
+    if p.ready is not None:
+        p.ready.wait(st)
     if PROFILE is not None:
         s_ev, e_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     if p.precision == TF32X3_SPLIT:
@@ -276,6 +319,32 @@ class _ConvBase(_Layer):
         self.bias = require_cuda(bias, "bias", torch.float32) if bias is not None else None
         return self
 
+    def build_index(self, src):
+        """Strided conv: output site set + neighbour map of `src` under this layer's geometry (cached on `src`, so a
+        prepare pass can build it ahead of the feature path, on another stream)."""
+        hit = src.strided.get(id(self))
+        if hit is not None:
+            return hit
+        K = self.kernel_size[0] * self.kernel_size[1] * self.kernel_size[2]
+        dev = src.coords.device
+        cap = self.out_cap if self.out_cap is not None else 4 * src.cap
+        out_coords = torch.empty((cap, 4), dtype=torch.int32, device=dev)
+        n_out = torch.empty((4,), dtype=torch.int32, device=dev)
+        nbr = torch.empty((cap, K), dtype=torch.int32, device=dev)
+        L = lib()
+        tab_in = src.table()
+        tab_out = torch.empty((L.p3d_sparse_table_bytes(cap),), dtype=torch.uint8, device=dev)
+        check(L.p3d_sparse_rulebook_conv_t(ptr(src.coords), ptr(src.num), src.cap, src.batch, host_ints(src.spatial),
+                                           host_ints(self.kernel_size), host_ints(self.stride),
+                                           host_ints(self.padding), ptr(tab_in), tab_in.numel(), ptr(out_coords),
+                                           ptr(n_out), cap, ptr(tab_out), tab_out.numel(), ptr(nbr), stream(dev)),
+              "sparse_rulebook_conv_t")
+        osp = [(src.spatial[a] + 2 * self.padding[a] - self.kernel_size[a]) // self.stride[a] + 1 for a in range(3)]
+        index = _IndexSet(out_coords, n_out, cap, src.batch, osp, table=tab_out)
+        index.counters = n_out
+        src.strided[id(self)] = (index, nbr)
+        return index, nbr
+
     def forward(self, x):
         if self.weight is None or isinstance(self.bias, str):
             raise RuntimeError("conv parameters not set")
@@ -283,6 +352,7 @@ class _ConvBase(_Layer):
         p = _Pending()
         p.x, p.K, p.cin, p.cout = x, K, self.in_channels, self.out_channels
         p.weight, p.scale, p.shift, p.residual, p.relu = self.weight, None, self.bias, None, False
+        p.ready = None
         p.precision = self.precision if self.precision is not None else _default_precision[0]
         if p.precision in (TF32X3, TF32X3_SPLIT):
             if not lib().p3d_sparse_conv_packed_weight_bytes(K, self.in_channels, self.out_channels) or K > 32:
@@ -292,25 +362,10 @@ class _ConvBase(_Layer):
         if self.subm:
             index = x.index
             p.nbr = index.subm_rulebook(self.kernel_size, self.key)
+            p.ready = index.ready.get(("subm", self.key if self.key is not None else "_anon", tuple(self.kernel_size)))
         else:
-            src = x.index
-            dev = src.coords.device
-            cap = self.out_cap if self.out_cap is not None else 4 * src.cap
-            out_coords = torch.empty((cap, 4), dtype=torch.int32, device=dev)
-            n_out = torch.empty((4,), dtype=torch.int32, device=dev)
-            nbr = torch.empty((cap, K), dtype=torch.int32, device=dev)
-            L = lib()
-            tab_in = src.table()
-            tab_out = torch.empty((L.p3d_sparse_table_bytes(cap),), dtype=torch.uint8, device=dev)
-            check(L.p3d_sparse_rulebook_conv_t(ptr(src.coords), ptr(src.num), src.cap, src.batch, host_ints(src.spatial),
-                                               host_ints(self.kernel_size), host_ints(self.stride),
-                                               host_ints(self.padding), ptr(tab_in), tab_in.numel(), ptr(out_coords),
-                                               ptr(n_out), cap, ptr(tab_out), tab_out.numel(), ptr(nbr), stream(dev)),
-                  "sparse_rulebook_conv_t")
-            osp = [(src.spatial[a] + 2 * self.padding[a] - self.kernel_size[a]) // self.stride[a] + 1 for a in range(3)]
-            index = _IndexSet(out_coords, n_out, cap, src.batch, osp, table=tab_out)
-            index.counters = n_out
-            p.nbr = nbr
+            index, p.nbr = self.build_index(x.index)
+            p.ready = x.index.ready.get(("conv", id(self)))
         p.num, p.cap = index.num, index.cap
         return SparseCooTensor(index, channels=self.out_channels, pending=p)
 
