@@ -308,15 +308,32 @@ __global__ void __launch_bounds__(128) small_cin_kernel(const float *__restrict_
 #pragma unroll
   for (int c = 0; c < COUT; ++c) acc[c] = 0.f;
   const int32_t *nb = nbr + row * K;
-  for (int k = 0; k < K; ++k) {
-    const int src = __ldg(nb + k);
-    if (src < 0) continue;
-    const float *x = in + static_cast<size_t>(src) * Cin;
-    const float *w = s_w + k * Cin * COUT;
-    for (int ci = 0; ci < Cin; ++ci) {
-      const float xv = __ldg(x + ci);
+  // Taps in batches of kTapBatch: first all neighbour indices of the batch, then all their (<= 8-channel) rows, then
+  // the FMAs - two memory latencies per batch instead of two per tap.  The FMA order (tap, then channel) and the
+  // skipping of missing neighbours are those of the plain loop, so results are bit-identical to it.
+  constexpr int kTapBatch = 9, kMaxCin = 8;
+  for (int k0 = 0; k0 < K; k0 += kTapBatch) {
+    int src[kTapBatch];
 #pragma unroll
-      for (int c = 0; c < COUT; ++c) acc[c] = fmaf(xv, w[ci * COUT + c], acc[c]);
+    for (int j = 0; j < kTapBatch; ++j) src[j] = (k0 + j < K) ? __ldg(nb + k0 + j) : -1;
+    float xv[kTapBatch][kMaxCin];
+#pragma unroll
+    for (int j = 0; j < kTapBatch; ++j) {
+      const float *x = in + static_cast<size_t>(src[j] < 0 ? 0 : src[j]) * Cin;
+#pragma unroll
+      for (int ci = 0; ci < kMaxCin; ++ci) xv[j][ci] = (src[j] >= 0 && ci < Cin) ? __ldg(x + ci) : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < kTapBatch; ++j) {
+      if (src[j] < 0) continue;
+      const float *w = s_w + (k0 + j) * Cin * COUT;
+#pragma unroll
+      for (int ci = 0; ci < kMaxCin; ++ci) {
+        if (ci < Cin) {
+#pragma unroll
+          for (int c = 0; c < COUT; ++c) acc[c] = fmaf(xv[j][ci], w[ci * COUT + c], acc[c]);
+        }
+      }
     }
   }
   float *o = out + row * COUT;

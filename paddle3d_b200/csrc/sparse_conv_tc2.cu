@@ -473,6 +473,10 @@ __global__ void __launch_bounds__(256)
                                long long n_cap, int C, const float *__restrict__ scale, const float *__restrict__ shift,
                                const float *__restrict__ residual_split, int relu, float *__restrict__ out_f32,
                                float *__restrict__ out_split) {
+  // programmatic dependent launch on both sides: this grid may start while the split-K conv drains (it waits here
+  // for the partial sums), and the next layer's prologue may start while this grid runs
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   const long long n = n_dev ? min(static_cast<long long>(n_dev[0]), n_cap) : n_cap;
   const int c4 = C / 4;
   const size_t slab = static_cast<size_t>(n_cap) * C / 4;
@@ -597,9 +601,22 @@ extern "C" int p3d_sparse_conv_gather_gemm_split_ws(const float *in_split, const
 #undef P3D_TC2_CASE
   if (rc != P3D_OK || !split) return rc;
   const long long fin_blocks = (n_out_cap * (Cout / 4) + 255) / 256;
-  tc2::rows_finalize_split_kernel<<<static_cast<unsigned int>(fin_blocks < kNumSMs * 8 ? fin_blocks : kNumSMs * 8), 256,
-                                    0, st>>>(k_f32, splits, n_out_dev, n_out_cap, Cout, scale, shift, residual_split,
-                                             relu, out_f32, out_split);
+  {
+    static const bool pdl = !(getenv("P3D_PDL") && atoi(getenv("P3D_PDL")) == 0);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(static_cast<unsigned int>(fin_blocks < kNumSMs * 8 ? fin_blocks : kNumSMs * 8));
+    cfg.blockDim = dim3(256);
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    const float *partial = k_f32;
+    const long long cap_ll = n_out_cap;
+    P3D_CUDA_CHECK(cudaLaunchKernelEx(&cfg, tc2::rows_finalize_split_kernel, partial, splits, n_out_dev, cap_ll, Cout,
+                                      scale, shift, residual_split, relu, out_f32, out_split));
+  }
   P3D_LAUNCH_CHECK();
   return P3D_OK;
 }
