@@ -26,17 +26,20 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t byt
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-  const long long t0 = clock64();
+  // try_wait with a suspend-time hint: the thread sleeps in hardware until the phase completes (or ~20 us pass)
+  // instead of polling - with the short default limit the waiting warps executed ~70 % of all instructions of the
+  // sparse-conv kernels (ncu: 1400 warp instructions per pipeline use, issue slots 50 % busy).
   uint32_t done;
+  int spins = 0;
   do {
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done)
-        : "r"(bar), "r"(parity)
+        : "r"(bar), "r"(parity), "r"(20000u)
         : "memory");
-    if (!done && clock64() - t0 > 4000000000ll) __trap();  // ~2 s: a protocol bug must not hang the GPU
+    if (!done && ++spins > 200000) __trap();  // seconds: a protocol bug must not hang the GPU
   } while (!done);
 }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
