@@ -177,6 +177,24 @@ def kernel_time_ms(fn, stream, iters):
     return s.elapsed_time(e) / iters
 
 
+def ncu_dram_bytes_per_frame():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the tensor-core sparse-conv launches of ONE frame, from the
+    committed `ncu --set full` capture of this command (profiles/r01_split_ncu_metrics.csv, 20 launches); None when
+    the capture is not in the tree."""
+    import csv
+    path = os.path.join(ROOT, "profiles", "r01_split_ncu_metrics.csv")
+    if not os.path.exists(path):
+        return None
+    rows = list(csv.reader(open(path)))
+    hdr, units = rows[0], rows[1]
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    total = 0.0
+    for name in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+        i = hdr.index(name)
+        total += sum(float(r[i]) for r in rows[2:]) * scale[units[i]]
+    return total
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -347,7 +365,8 @@ def main():
         if tc_ms > 0:
             ach = tc_flops / (tc_ms * 1e-3) / 1e12
             roof = {"bound": "tensor", "kernel": ("tc2::gather_gemm_split_kernel" if precision == sp.TF32X3_SPLIT else "tc::gather_gemm_tf32x3_kernel") + " (all tensor-core sparse convs of one frame)",
-                    "achieved": ach, "peak": bf16_peak, "unit": "TFLOP/s", "frac": ach / bf16_peak, "traffic": None,
+                    "achieved": ach, "peak": bf16_peak, "unit": "TFLOP/s", "frac": ach / bf16_peak,
+                    "traffic": ncu_dram_bytes_per_frame(),
                     "algorithmic_flops": tc_flops, "ms": tc_ms,
                     "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst)" if pk else "fallback 1.59 PFLOP/s",
                     "note": "achieved counts ALGORITHMIC flops 2*pairs*Cin*Cout; the kernel executes 3 tf32 MMAs per product "

@@ -21,7 +21,7 @@ namespace p3d {
 // row_stride = words per mask row.  blockDim.x must be a multiple of 32 and >= 64.
 __device__ inline int nms_greedy_cta(const unsigned long long *__restrict__ mask, int n, int row_stride,
                                      int32_t *__restrict__ keep, unsigned long long *s_removed,
-                                     unsigned long long *s_misc) {
+                                     unsigned long long *s_misc, int limit = 0x7fffffff) {
   const int col_blocks = (n + 63) / 64;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   for (int j = tid; j < col_blocks; j += blockDim.x) s_removed[j] = 0ull;
@@ -59,6 +59,9 @@ __device__ inline int nms_greedy_cta(const unsigned long long *__restrict__ mask
     }
     kept_total += __popcll(kept);
     __syncthreads();
+    // a caller that consumes only the first `limit` kept boxes (in score order) does not need the later tiles:
+    // the first `limit` entries of keep[] are final once kept_total reaches it (uniform exit: same value in all threads)
+    if (kept_total >= limit) break;
   }
   return kept_total;
 }

@@ -187,7 +187,7 @@ __global__ void __launch_bounds__(256) cpp_greedy_kernel(CppAttrs at, CppWs w) {
   const int t = blockIdx.x;
   const int n = min(w.cnt[t], at.pre_max);
   const int k = nms_greedy_cta(w.mask + static_cast<size_t>(t) * at.pre_max * at.cbmax, n, at.cbmax,
-                               w.keep + static_cast<size_t>(t) * at.pre_max, s_dyn, s_misc);
+                               w.keep + static_cast<size_t>(t) * at.pre_max, s_dyn, s_misc, at.post_max);
   if (threadIdx.x == 0) w.nkeep[t] = k;
 }
 
