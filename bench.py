@@ -201,7 +201,7 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--precision", default="tf32x3_split", choices=["fp32", "tf32x3", "tf32x3_split"])
+    ap.add_argument("--precision", default="tf32x3_split", choices=["fp32", "tf32x3", "tf32x3_split", "tf32x3_tma"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -228,7 +228,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     cfg = synth.C3
-    precision = {"tf32x3": sp.TF32X3, "tf32x3_split": sp.TF32X3_SPLIT, "fp32": sp.FP32}[args.precision]
+    precision = {"tf32x3": sp.TF32X3, "tf32x3_split": sp.TF32X3_SPLIT, "tf32x3_tma": sp.TF32X3_TMA, "fp32": sp.FP32}[args.precision]
     caps = [int(x) for x in os.environ["P3D_LEVEL_CAPS"].split(",")] if os.environ.get("P3D_LEVEL_CAPS") else None
     pipe = CenterPointHotPath(cfg, dev, precision=precision, seed=0, level_caps=caps)
     if world > 1:  # weights only: one broadcast over NVLink at start, no per-frame collective
@@ -346,10 +346,10 @@ def main():
             ms = s_ev.elapsed_time(e_ev)
             fl = 2.0 * pairs * cin * cout
             layers.append({"cin": cin, "cout": cout, "rows": rows, "pairs": pairs, "ms": round(ms, 4),
-                           "precision": "tf32x3" if prec in (sp.TF32X3, sp.TF32X3_SPLIT) else "fp32", "gflop": round(fl / 1e9, 3)})
+                           "precision": "tf32x3" if prec in (sp.TF32X3, sp.TF32X3_SPLIT, sp.TF32X3_TMA) else "fp32", "gflop": round(fl / 1e9, 3)})
             conv_ms += ms
             conv_flops += fl
-            if prec in (sp.TF32X3, sp.TF32X3_SPLIT):
+            if prec in (sp.TF32X3, sp.TF32X3_SPLIT, sp.TF32X3_TMA):
                 tc_ms += ms
                 tc_flops += fl
         extra["stage_ms_eager"] = stage
@@ -364,7 +364,7 @@ def main():
                     "algorithmic_bytes": vox_bytes, "ms": ms_vox, "peak_source": peak_src}
         if tc_ms > 0:
             ach = tc_flops / (tc_ms * 1e-3) / 1e12
-            roof = {"bound": "tensor", "kernel": ("tc2::gather_gemm_split_kernel" if precision == sp.TF32X3_SPLIT else "tc::gather_gemm_tf32x3_kernel") + " (all tensor-core sparse convs of one frame)",
+            roof = {"bound": "tensor", "kernel": ("tc2::gather_gemm_split_kernel" if precision in (sp.TF32X3_SPLIT, sp.TF32X3_TMA) else "tc::gather_gemm_tf32x3_kernel") + " (all tensor-core sparse convs of one frame)",
                     "achieved": ach, "peak": bf16_peak, "unit": "TFLOP/s", "frac": ach / bf16_peak,
                     "traffic": ncu_dram_bytes_per_frame(),
                     "algorithmic_flops": tc_flops, "ms": tc_ms,

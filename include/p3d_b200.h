@@ -241,6 +241,14 @@ int p3d_sparse_conv_gather_gemm_split_ws(const float *in_split, const int32_t *n
                                          const float *scale, const float *shift, const float *residual_split, int relu,
                                          float *out_f32, float *out_split, void *workspace, size_t workspace_bytes,
                                          p3d_stream_t stream);
+/* EXPERIMENTAL (round-2 groundwork, not on the default path): the same layer with the row gather done by the TMA
+ * engine (cp.async.bulk.tensor tile::gather4 through a tensor map over in_split [n_in_rows][2*Cin]) instead of
+ * cp.async from 8 producer warps.  Cin >= 32 only (P3D_ERR_UNSUPPORTED otherwise). */
+int p3d_sparse_conv_gather_gemm_split_tma(const float *in_split, int64_t n_in_rows, const int32_t *nbr,
+                                          const int32_t *n_out_dev, int64_t n_out_cap, int K, int Cin, int Cout,
+                                          const float *packed_weight, const float *scale, const float *shift,
+                                          const float *residual_split, int relu, float *out_f32, float *out_split,
+                                          void *workspace, size_t workspace_bytes, p3d_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -17,6 +17,8 @@
 // barrier skeleton costs 550-690 cycles per use with 4 producer warps), so the row gather is spread over 8 warps
 // (or 4 CTAs per SM for the narrow layers) and the stage index restarts at 0 for every work item, which keeps the
 // operand addresses on the uniform datapath.
+#include <cuda.h>  // CUtensorMap (types only: the encoder is fetched with cudaGetDriverEntryPoint)
+
 #include "tc_common.cuh"
 
 namespace p3d {
@@ -111,9 +113,22 @@ __device__ __forceinline__ void umma_commit_elect(uint32_t bar) {
       : "memory");
 }
 
-template <int CIN, int COUT>
+// TMA row gather (experimental, TMA = true, Cin >= 32): 4 rows x 128 bytes of the split rows per instruction, written
+// by the TMA engine in the SWIZZLE_128B pattern of the tensor map; a negative (missing neighbour) or out-of-range row
+// index is out of bounds for the map and arrives as zeros.
+__device__ __forceinline__ void tma_gather4(uint32_t dst, const CUtensorMap *map, int col, int r0, int r1, int r2, int r3,
+                                            uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cta.global.tile::gather4.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, "
+      "%5, %6}], [%7];" ::"r"(dst),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(col), "r"(r0), "r"(r1), "r"(r2), "r"(r3), "r"(bar)
+      : "memory");
+}
+
+template <int CIN, int COUT, bool TMA>
 __global__ void __launch_bounds__(Cfg<CIN, COUT>::THREADS, Cfg<CIN, COUT>::MIN_CTAS)
-    gather_gemm_split_kernel(const float *__restrict__ in_split, const int32_t *__restrict__ nbr,
+    gather_gemm_split_kernel(const __grid_constant__ CUtensorMap in_map, const float *__restrict__ in_split,
+                             const int32_t *__restrict__ nbr,
                              const int32_t *__restrict__ n_out_dev, long long n_cap, int K, int splits,
                              const float *__restrict__ packed_w, const float *__restrict__ scale,
                              const float *__restrict__ shift, const float *__restrict__ residual_split, int relu,
@@ -149,8 +164,9 @@ __global__ void __launch_bounds__(Cfg<CIN, COUT>::THREADS, Cfg<CIN, COUT>::MIN_C
   if (dbg0) dbg[4096 + 256] = clock64();
   if (tid == kMmaWarp * 32) {
     for (int s = 0; s < C::STAGES; ++s) {
-      mbar_init(smem_u32(&s_bar[kF + s]), C::NPW * 32 + 1);  // cp.async completions of every producer thread + the
-                                                             // weight copy's expect_tx arrival
+      // cp.async completions of every producer thread + the weight copy's expect_tx arrival; with the TMA gather the
+      // one expect_tx arrival covers rows and weights
+      mbar_init(smem_u32(&s_bar[kF + s]), TMA ? 1 : C::NPW * 32 + 1);
       mbar_init(smem_u32(&s_bar[kE + s]), 1);                // tcgen05.commit
     }
     mbar_init(smem_u32(&s_bar[kTF]), 1);
@@ -223,7 +239,7 @@ __global__ void __launch_bounds__(Cfg<CIN, COUT>::THREADS, Cfg<CIN, COUT>::MIN_C
       // contiguous bytes of the swizzled tiles: no bank conflicts.
       const int sub = lane >> 3;
       int s = 0, u = 0;
-      for (int t = 0; t < K; ++t) {
+      for (int t = 0; t < (TMA ? 0 : K); ++t) {  // (the TMA variant has no producer loop: warp NPW + 1 gathers)
         if (!((active >> t) & 1u)) continue;
         int src[C::QN];
 #pragma unroll
@@ -401,7 +417,36 @@ __global__ void __launch_bounds__(Cfg<CIN, COUT>::THREADS, Cfg<CIN, COUT>::MIN_C
       tc_fence_before();
     } else {
       // ---------------------------------------------------------------- weight TMA (one lane)
-      if (lane == 0) {
+      if (TMA) {
+        // whole warp: lane l gathers rows 4l .. 4l+3 of the tile (hi line and lo line of the 32-channel slice), lane 0
+        // also posts the byte count and copies the weights of the use
+        int s = 0, u = 0;
+        for (int t = 0; t < K; ++t) {
+          if (!((active >> t) & 1u)) continue;
+          int r[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) r[q] = (lane * 4 + q) < rows ? s_nbr[(lane * 4 + q) * K + t] : -1;
+          for (int g = 0; g < C::G; ++g, ++u) {
+            mbar_wait(smem_u32(&s_bar[kE + s]), (ph >> s) & 1u);
+            ph ^= 1u << s;
+            const uint32_t st = ring + static_cast<uint32_t>(s * C::STAGE), bar = smem_u32(&s_bar[kF + s]);
+            if (lane == 0) {
+              if (dbg && blockIdx.x == 0 && use_base + u < 512) dbg[(use_base + u) * 8 + 2] = clock64();
+              mbar_arrive_expect_tx(bar, static_cast<uint32_t>(((flags & 2) ? 0 : C::A_STAGE) + ((flags & 1) ? 0 : C::B_STAGE)));
+              if (!(flags & 1))
+                bulk_g2s(st + C::A_STAGE, packed_w + (static_cast<size_t>(t) * CIN + g * C::KC) * (2 * COUT),
+                         static_cast<uint32_t>(C::B_STAGE), bar);
+            }
+            __syncwarp();
+            if (!(flags & 2)) {
+              tma_gather4(st + lane * 512, &in_map, g * 32, r[0], r[1], r[2], r[3], bar);                    // hi
+              tma_gather4(st + C::A_TILE + lane * 512, &in_map, CIN + g * 32, r[0], r[1], r[2], r[3], bar);  // lo
+            }
+            if (dbg && blockIdx.x == 0 && lane == 0 && use_base + u < 512) dbg[(use_base + u) * 8 + 3] = clock64();
+            s = (s + 1 == C::STAGES) ? 0 : s + 1;
+          }
+        }
+      } else if (lane == 0) {
         int s = 0, u = 0;
         for (int t = 0; t < K; ++t) {
           if (!((active >> t) & 1u)) continue;
@@ -436,14 +481,44 @@ __global__ void __launch_bounds__(Cfg<CIN, COUT>::THREADS, Cfg<CIN, COUT>::MIN_C
   }
 }
 
-template <int CIN, int COUT>
+// Tensor map of the split rows [n_rows][2 * C] fp32 for tile::gather4: box = 32 columns (one 128-byte line) x 1 row,
+// SWIZZLE_128B, out-of-bounds reads (missing neighbours) filled with zeros.
+inline int make_rows_map(const float *rows, int64_t n_rows, int C, CUtensorMap *map) {
+  using Encode = CUresult (*)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                              const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                              CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static Encode encode = nullptr;
+  if (!encode) {
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qr) != cudaSuccess || !fn)
+      return P3D_ERR_UNSUPPORTED;
+    encode = reinterpret_cast<Encode>(fn);
+  }
+  const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(2 * C), static_cast<cuuint64_t>(n_rows)};
+  const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(2 * C) * sizeof(float)};
+  const cuuint32_t box[2] = {32u, 1u}, estride[2] = {1u, 1u};
+  const CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(rows), gdim, gstride, box, estride,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? P3D_OK : P3D_ERR_INVALID_ARG;
+}
+
+template <int CIN, int COUT, bool TMA = false>
 int launch(const float *in_split, const int32_t *nbr, const int32_t *n_out_dev, int64_t n_cap, int K,
            const float *packed, const float *scale, const float *shift, const float *residual_split, int relu,
-           float *out_f32, float *out_split, cudaStream_t st, long long *dbg = nullptr, int splits = 1) {
+           float *out_f32, float *out_split, cudaStream_t st, long long *dbg = nullptr, int splits = 1,
+           int64_t n_in_rows = 0) {
   using C = Cfg<CIN, COUT>;
+  CUtensorMap in_map = {};
+  if (TMA) {
+    static_assert(!TMA || C::KC == 32, "the TMA gather is written for 32-channel uses");
+    const int rc = make_rows_map(in_split, n_in_rows, CIN, &in_map);
+    if (rc != P3D_OK) return rc;
+  }
   const size_t smem = static_cast<size_t>(C::STAGES) * C::STAGE + static_cast<size_t>(kM) * K * sizeof(int32_t) + 1024;
   if (smem > 227 * 1024) return P3D_ERR_UNSUPPORTED;
-  auto kern = gather_gemm_split_kernel<CIN, COUT>;
+  auto kern = gather_gemm_split_kernel<CIN, COUT, TMA>;
   P3D_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
   const long long work = ((n_cap + kM - 1) / kM) * splits;
   const long long slots = static_cast<long long>(kNumSMs) * C::MIN_CTAS;
@@ -460,7 +535,7 @@ int launch(const float *in_split, const int32_t *nbr, const int32_t *n_out_dev, 
   cfg.attrs = attr;
   cfg.numAttrs = pdl ? 1 : 0;
   const long long n_cap_ll = n_cap;
-  P3D_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, in_split, nbr, n_out_dev, n_cap_ll, K, splits, packed, scale, shift,
+  P3D_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern, in_map, in_split, nbr, n_out_dev, n_cap_ll, K, splits, packed, scale, shift,
                                     residual_split, relu, out_f32, out_split, dbg));
   P3D_LAUNCH_CHECK();
   return P3D_OK;
@@ -562,12 +637,10 @@ extern "C" int p3d_rows_convert_layout(const float *src, int src_layout, const i
   return P3D_OK;
 }
 
-extern "C" int p3d_sparse_conv_gather_gemm_split_ws(const float *in_split, const int32_t *nbr,
-                                                    const int32_t *n_out_dev, int64_t n_out_cap, int K, int Cin,
-                                                    int Cout, const float *packed_weight, const float *scale,
-                                                    const float *shift, const float *residual_split, int relu,
-                                                    float *out_f32, float *out_split, void *workspace,
-                                                    size_t workspace_bytes, p3d_stream_t stream) {
+static int split_conv(const float *in_split, int64_t n_in_rows, bool tma, const int32_t *nbr, const int32_t *n_out_dev,
+                      int64_t n_out_cap, int K, int Cin, int Cout, const float *packed_weight, const float *scale,
+                      const float *shift, const float *residual_split, int relu, float *out_f32, float *out_split,
+                      void *workspace, size_t workspace_bytes, p3d_stream_t stream) {
   if (n_out_cap < 0 || K < 1 || K > 32 || !packed_weight || (!out_f32 && !out_split) || (n_out_cap && (!in_split || !nbr)))
     return P3D_ERR_INVALID_ARG;
   if (n_out_cap == 0) return P3D_OK;
@@ -588,9 +661,13 @@ extern "C" int p3d_sparse_conv_gather_gemm_split_ws(const float *in_split, const
   const int k_relu = split ? 0 : relu, k_splits = split ? splits : 1;
   int rc = P3D_ERR_UNSUPPORTED;
 #define P3D_TC2_CASE(CI, CO)                                                                                           \
-  if (Cin == CI && Cout == CO)                                                                                         \
+  if (!tma && Cin == CI && Cout == CO)                                                                                 \
     rc = tc2::launch<CI, CO>(in_split, nbr, n_out_dev, n_out_cap, K, packed_weight, k_scale, k_shift, k_res, k_relu,    \
                              k_f32, k_split, st, nullptr, k_splits);
+#define P3D_TC2_TMA_CASE(CI, CO)                                                                                       \
+  if (tma && Cin == CI && Cout == CO)                                                                                  \
+    rc = tc2::launch<CI, CO, true>(in_split, nbr, n_out_dev, n_out_cap, K, packed_weight, k_scale, k_shift, k_res,      \
+                                   k_relu, k_f32, k_split, st, nullptr, k_splits, n_in_rows);
   P3D_TC2_CASE(16, 16)
   P3D_TC2_CASE(16, 32)
   P3D_TC2_CASE(32, 32)
@@ -598,7 +675,13 @@ extern "C" int p3d_sparse_conv_gather_gemm_split_ws(const float *in_split, const
   P3D_TC2_CASE(64, 64)
   P3D_TC2_CASE(64, 128)
   P3D_TC2_CASE(128, 128)
+  P3D_TC2_TMA_CASE(32, 32)
+  P3D_TC2_TMA_CASE(32, 64)
+  P3D_TC2_TMA_CASE(64, 64)
+  P3D_TC2_TMA_CASE(64, 128)
+  P3D_TC2_TMA_CASE(128, 128)
 #undef P3D_TC2_CASE
+#undef P3D_TC2_TMA_CASE
   if (rc != P3D_OK || !split) return rc;
   const long long fin_blocks = (n_out_cap * (Cout / 4) + 255) / 256;
   {
@@ -619,6 +702,27 @@ extern "C" int p3d_sparse_conv_gather_gemm_split_ws(const float *in_split, const
   }
   P3D_LAUNCH_CHECK();
   return P3D_OK;
+}
+
+extern "C" int p3d_sparse_conv_gather_gemm_split_ws(const float *in_split, const int32_t *nbr,
+                                                    const int32_t *n_out_dev, int64_t n_out_cap, int K, int Cin,
+                                                    int Cout, const float *packed_weight, const float *scale,
+                                                    const float *shift, const float *residual_split, int relu,
+                                                    float *out_f32, float *out_split, void *workspace,
+                                                    size_t workspace_bytes, p3d_stream_t stream) {
+  return split_conv(in_split, 0, false, nbr, n_out_dev, n_out_cap, K, Cin, Cout, packed_weight, scale, shift,
+                    residual_split, relu, out_f32, out_split, workspace, workspace_bytes, stream);
+}
+
+extern "C" int p3d_sparse_conv_gather_gemm_split_tma(const float *in_split, int64_t n_in_rows, const int32_t *nbr,
+                                                     const int32_t *n_out_dev, int64_t n_out_cap, int K, int Cin,
+                                                     int Cout, const float *packed_weight, const float *scale,
+                                                     const float *shift, const float *residual_split, int relu,
+                                                     float *out_f32, float *out_split, void *workspace,
+                                                     size_t workspace_bytes, p3d_stream_t stream) {
+  if (n_in_rows < 1 || Cin < 32) return P3D_ERR_UNSUPPORTED;
+  return split_conv(in_split, n_in_rows, true, nbr, n_out_dev, n_out_cap, K, Cin, Cout, packed_weight, scale, shift,
+                    residual_split, relu, out_f32, out_split, workspace, workspace_bytes, stream);
 }
 
 extern "C" int p3d_sparse_conv_gather_gemm_split(const float *in_split, const int32_t *nbr, const int32_t *n_out_dev,

@@ -25,10 +25,11 @@ from .._mem import ptr, require_cuda, stream, workspace
 from . import pillar_scatter as _ps
 
 # FP32         exact fp32 FMA on CUDA cores
-# TF32X3       tcgen05 3xTF32 on plain fp32 rows: the tf32 hi/lo split happens inside the gather loop (fastest today)
-# TF32X3_SPLIT tcgen05 3xTF32 on split-layout rows [n][2][C]: cp.async gathers, persistent tiles, split done once in
-#              the producing layer's epilogue (experimental: measured slower than TF32X3)
-FP32, TF32X3, TF32X3_SPLIT = 0, 1, 2
+# TF32X3       tcgen05 3xTF32 on plain fp32 rows: the tf32 hi/lo split happens inside the gather loop
+# TF32X3_SPLIT tcgen05 3xTF32 on split-layout rows [n][2][C]: whole-line cp.async gathers, persistent tiles, split done
+#              once in the producing layer's epilogue (fastest measured, what the pipeline and the bench use)
+# TF32X3_TMA   experimental: TF32X3_SPLIT with the row gather of the Cin >= 32 layers done by TMA tile::gather4
+FP32, TF32X3, TF32X3_SPLIT, TF32X3_TMA = 0, 1, 2, 3
 ROWS_F32, ROWS_SPLIT = 0, 1           # activation layouts: [n, C] fp32 | [n][2][C] tf32 hi/lo halves
 _default_precision = [FP32]
 
@@ -203,7 +204,7 @@ def _run(p, t, want):
         p.ready.wait(st)
     if PROFILE is not None:
         s_ev, e_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    if p.precision == TF32X3_SPLIT:
+    if p.precision in (TF32X3_SPLIT, TF32X3_TMA):
         xin = p.x.get(ROWS_SPLIT)
         res = p.residual.get(ROWS_SPLIT) if p.residual is not None else None
         out_f32 = torch.empty((p.cap, p.cout), dtype=torch.float32, device=dev) if want == ROWS_F32 else None
@@ -212,10 +213,16 @@ def _run(p, t, want):
             s_ev.record(st)
         wsb = L.p3d_sparse_conv_splitk_workspace_bytes(p.cap, p.cin, p.cout)  # > 0 for the wide (split-K) layers
         ws = workspace(wsb, dev, "splitk") if wsb else None
-        check(L.p3d_sparse_conv_gather_gemm_split_ws(ptr(xin), ptr(p.nbr), ptr(p.num), p.cap, p.K, p.cin, p.cout,
-                                                     ptr(p.weight), ptr(p.scale), ptr(p.shift), ptr(res), int(p.relu),
-                                                     ptr(out_f32), ptr(out_split), ptr(ws), wsb, stream(dev)),
-              "sparse_conv_gather_gemm_split_ws")
+        if p.precision == TF32X3_TMA and p.cin >= 32:
+            check(L.p3d_sparse_conv_gather_gemm_split_tma(ptr(xin), xin.shape[0], ptr(p.nbr), ptr(p.num), p.cap, p.K,
+                                                          p.cin, p.cout, ptr(p.weight), ptr(p.scale), ptr(p.shift),
+                                                          ptr(res), int(p.relu), ptr(out_f32), ptr(out_split), ptr(ws),
+                                                          wsb, stream(dev)), "sparse_conv_gather_gemm_split_tma")
+        else:
+            check(L.p3d_sparse_conv_gather_gemm_split_ws(ptr(xin), ptr(p.nbr), ptr(p.num), p.cap, p.K, p.cin, p.cout,
+                                                         ptr(p.weight), ptr(p.scale), ptr(p.shift), ptr(res),
+                                                         int(p.relu), ptr(out_f32), ptr(out_split), ptr(ws), wsb,
+                                                         stream(dev)), "sparse_conv_gather_gemm_split_ws")
         t._vals[ROWS_F32], t._vals[ROWS_SPLIT] = out_f32, out_split
     else:
         xin = p.x.get(ROWS_F32)
@@ -354,7 +361,7 @@ class _ConvBase(_Layer):
         p.weight, p.scale, p.shift, p.residual, p.relu = self.weight, None, self.bias, None, False
         p.ready = None
         p.precision = self.precision if self.precision is not None else _default_precision[0]
-        if p.precision in (TF32X3, TF32X3_SPLIT):
+        if p.precision in (TF32X3, TF32X3_SPLIT, TF32X3_TMA):
             if not lib().p3d_sparse_conv_packed_weight_bytes(K, self.in_channels, self.out_channels) or K > 32:
                 p.precision = FP32  # e.g. the 5-channel input layer stays on the exact fp32 path
             else:

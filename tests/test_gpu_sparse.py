@@ -2,12 +2,18 @@
 Tolerance: 1e-4 relative (fp32), BASELINE.json north_star.  PARITY UNPINNED by the reference (the
 arithmetic is PaddlePaddle's); the oracle restatement is itself checked against dense fp64 conv3d in
 tests/test_oracle.py."""
+import os
+
 import numpy as np
 import pytest
 
 from paddle3d_b200 import synth
 
 pytestmark = pytest.mark.gpu
+
+# 0 fp32 CUDA cores, 1 tcgen05 on fp32 rows, 2 tcgen05 on split rows (default); 3 = the experimental TMA-gather variant,
+# only with P3D_EXPERIMENTAL=1
+PRECISIONS = [0, 1, 2] + ([3] if os.environ.get("P3D_EXPERIMENTAL") == "1" else [])
 
 
 def _t(cuda, a):
@@ -28,7 +34,7 @@ def _rand_sites(rng, B, D, H, W, p):
     return c
 
 
-@pytest.mark.parametrize("precision", [0, 1, 2])
+@pytest.mark.parametrize("precision", PRECISIONS)
 @pytest.mark.parametrize("subm,ks,st,pd,cin,cout", [
     (True, 3, 1, 1, 5, 16), (True, 3, 1, 1, 16, 16), (True, 3, 1, 1, 64, 64), (True, 3, 1, 1, 128, 128),
     (False, 3, 2, 1, 16, 32), (False, 3, 2, [0, 1, 1], 64, 128), (False, (3, 1, 1), (2, 1, 1), 0, 128, 128),
@@ -120,7 +126,7 @@ def _oracle_resnet(oracle_mod, net, coords, feats, B):
     return oracle_mod.sparse_to_dense_bev(c, f, B, sp_), pairs
 
 
-@pytest.mark.parametrize("precision", [0, 1, 2])
+@pytest.mark.parametrize("precision", PRECISIONS)
 def test_sparse_resnet3d_small(cuda, oracle_mod, precision):
     """Whole 21-conv backbone on a reduced grid (41 x 176 x 176 -> 2 x 22 x 22), lidar-like occupancy."""
     from paddle3d_b200.layers import SparseResNet3D
