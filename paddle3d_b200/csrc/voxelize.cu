@@ -32,6 +32,8 @@ namespace {
 constexpr unsigned long long kEmpty = ~0ull;
 constexpr int kInf = 0x7fffffff;
 constexpr int kScanBlock = 1024;
+constexpr int kScanItems = 4;                       // consecutive points per thread of the rank scan
+constexpr int kScanTile = kScanBlock * kScanItems;  // points per block: 74 look-back hops at 300k points, not 293
 
 struct VoxGeom {
   float min_x, min_y, min_z;
@@ -56,7 +58,7 @@ VoxWs carve(void *ws, int64_t n, int P, int V) {
   w.cap = next_pow2(static_cast<uint64_t>(n > 512 ? n : 512) * 2);
   w.shift = 32;
   for (uint32_t x = w.cap; x > 1; x >>= 1) --w.shift;
-  w.nblocks = div_up(n > 0 ? n : 1, kScanBlock);
+  w.nblocks = div_up(n > 0 ? n : 1, kScanTile);
   w.table = c.take<unsigned long long>(w.cap);
   w.desc = c.take<unsigned long long>(w.nblocks + 1);
   w.pt_slot = c.take<int32_t>(n > 0 ? n : 1);
@@ -141,32 +143,48 @@ __global__ void __launch_bounds__(kScanBlock) vox_rank_kernel(const unsigned lon
   if (threadIdx.x == 0) s_bid = static_cast<unsigned int>(atomicAdd(&desc[0], 1ull));
   __syncthreads();
   const unsigned int bid = s_bid;
-  const int i = static_cast<int>(bid) * kScanBlock + threadIdx.x;
-  int slot = -1, flag = 0;
-  unsigned long long entry = 0;
-  if (i < n) {
-    slot = pt_slot[i];
-    if (slot >= 0) {
-      entry = table[slot];
-      flag = (static_cast<uint32_t>(entry) == static_cast<uint32_t>(i));
-    }
+  const int i0 = static_cast<int>(bid) * kScanTile + threadIdx.x * kScanItems;
+  int slot[kScanItems];
+  unsigned long long entry[kScanItems];
+  if (i0 + kScanItems <= n) {
+    const int4 v4 = *reinterpret_cast<const int4 *>(pt_slot + i0);  // i0 is a multiple of 4, pt_slot 256-byte aligned
+    slot[0] = v4.x;
+    slot[1] = v4.y;
+    slot[2] = v4.z;
+    slot[3] = v4.w;
+  } else {
+#pragma unroll
+    for (int k = 0; k < kScanItems; ++k) slot[k] = (i0 + k < n) ? pt_slot[i0 + k] : -1;
   }
-  // block exclusive scan of flags
+  static_assert(kScanItems == 4, "the vector load above is written for 4 items per thread");
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k) entry[k] = slot[k] >= 0 ? table[slot[k]] : 0ull;
+  unsigned int flags = 0u;  // bit k: point i0 + k is the first point of its cell
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k)
+    if (slot[k] >= 0 && static_cast<uint32_t>(entry[k]) == static_cast<uint32_t>(i0 + k)) flags |= 1u << k;
+  const int cnt = __popc(flags);
+  // block exclusive scan of the per-thread counts
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const unsigned bal = __ballot_sync(0xffffffffu, flag);
-  const int in_warp = __popc(bal & ((1u << lane) - 1));
-  if (lane == 0) s_warp[wid] = __popc(bal);
+  int inc = cnt;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, inc, d);
+    if (lane >= d) inc += t;
+  }
+  const int in_warp = inc - cnt;
+  if (lane == 31) s_warp[wid] = inc;
   __syncthreads();
   if (wid == 0) {
-    int v = s_warp[lane];
-    int inc = v;
+    const int v = s_warp[lane];
+    int winc = v;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-      int t = __shfl_up_sync(0xffffffffu, inc, d);
-      if (lane >= d) inc += t;
+      const int t = __shfl_up_sync(0xffffffffu, winc, d);
+      if (lane >= d) winc += t;
     }
-    s_warp[lane] = inc - v;  // exclusive warp offsets
-    const int aggregate = __shfl_sync(0xffffffffu, inc, 31);
+    s_warp[lane] = winc - v;  // exclusive warp offsets
+    const int aggregate = __shfl_sync(0xffffffffu, winc, 31);
     if (lane == 0) {
       // decoupled look-back: status 1 = block aggregate, 2 = inclusive prefix
       int prefix = 0;
@@ -194,12 +212,15 @@ __global__ void __launch_bounds__(kScanBlock) vox_rank_kernel(const unsigned lon
     }
   }
   __syncthreads();
-  if (flag) {
-    const int rank = s_prefix + s_warp[wid] + in_warp;
+  int rank = s_prefix + s_warp[wid] + in_warp;
+#pragma unroll
+  for (int k = 0; k < kScanItems; ++k) {
+    if (!((flags >> k) & 1u)) continue;
     const int v = rank < max_voxels ? rank : -1;
-    slot_vox[slot] = v;
+    ++rank;
+    slot_vox[slot[k]] = v;
     if (v >= 0) {
-      const int cell = static_cast<int>(entry >> 32);
+      const int cell = static_cast<int>(entry[k] >> 32);
       const int cx = cell % g.gx;
       const int r = cell / g.gx;
       int32_t *c = coords + static_cast<size_t>(v) * coord_stride;
@@ -344,7 +365,7 @@ __global__ void __launch_bounds__(256) voxel_mean_kernel(const float *__restrict
 }
 
 int check_geom(const float *vs, const float *pcr, int64_t n, int F, int P, int V, VoxGeom *g) {
-  if (!vs || !pcr || n < 0 || n > INT_MAX - kScanBlock || F < 3 || P < 1 || V < 1) return P3D_ERR_INVALID_ARG;
+  if (!vs || !pcr || n < 0 || n > INT_MAX - kScanTile || F < 3 || P < 1 || V < 1) return P3D_ERR_INVALID_ARG;
   g->min_x = pcr[0];
   g->min_y = pcr[1];
   g->min_z = pcr[2];
