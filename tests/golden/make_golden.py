@@ -6,6 +6,9 @@
                    points_to_voxel (paddle3d/transforms/functional.py:118-150, AST-extracted and exec'd —
                    importing the package would import paddle) on seeded inputs; the two must agree.
   iou_bev.npz      boxes_iou_bev_cpu (iou3d_cpu.cpp:241-264, compiled unmodified).
+  sweeps.npz       LoadPointCloud.__call__ (paddle3d/transforms/reader.py:116-167, AST-extracted: importing the module
+                   would import paddle) on three seeded .bin files; stores the files' contents, the transforms, the
+                   sweep order the reference's np.random.choice drew and the merged cloud.
 
 Usage: python tests/golden/make_golden.py
 """
@@ -47,8 +50,54 @@ def run_numba(fn, pts, cfg, P, V):
     return voxels, coords, npv, np.array([nv], np.int32)
 
 
+def reference_load_point_cloud():
+    """The reference's LoadPointCloud class body (methods only), exec'd without its paddle-importing module."""
+    src = open(os.path.join(REF, "paddle3d/transforms/reader.py")).read()
+    tree = ast.parse(src)
+    cls = [n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == "LoadPointCloud"][0]
+    code = "class LoadPointCloud:\n" + "\n".join(
+        "    " + line for fn in cls.body if isinstance(fn, ast.FunctionDef)
+        for line in ast.get_source_segment(src, fn).splitlines())
+    import typing
+    ns = {"np": np, "Union": typing.Union, "List": typing.List, "Sample": object, "PointCloud": lambda x: x}
+    exec(code, ns)
+    return ns["LoadPointCloud"]
+
+
+def make_sweeps_golden():
+    import tempfile
+    from types import SimpleNamespace as NS
+    rng = np.random.default_rng(21)
+    clouds = [np.concatenate([rng.uniform(-3, 3, size=(n, 3)), rng.uniform(0, 255, size=(n, 1)),
+                              rng.integers(0, 32, size=(n, 1))], 1).astype(np.float32) for n in (500, 400, 300, 350)]
+    mats, lags = [], [0.05, 0.1, 0.15]
+    for k in range(3):
+        a = 0.01 * (k + 1)
+        m = np.eye(4)
+        m[:2, :2] = [[np.cos(a), -np.sin(a)], [np.sin(a), np.cos(a)]]
+        m[:3, 3] = [0.3 * (k + 1), -0.1 * k, 0.02]
+        mats.append(m)
+    mats[1] = None  # a sweep without transform
+    with tempfile.TemporaryDirectory() as d:
+        paths = []
+        for i, c in enumerate(clouds):
+            paths.append(os.path.join(d, "c%d.bin" % i))
+            c.tofile(paths[-1])
+        sweeps = [NS(path=paths[i + 1], meta=NS(ref_from_curr=mats[i], time_lag=lags[i])) for i in range(3)]
+        sample = NS(modality="lidar", data=None, path=paths[0], sweeps=sweeps)
+        cls = reference_load_point_cloud()
+        np.random.seed(1)
+        order = np.random.choice(3, 3, replace=False)  # what the call below will draw
+        np.random.seed(1)
+        out = cls(dim=5, use_dim=[0, 1, 2, 4], use_time_lag=True, sweep_remove_radius=1)(sample).data
+    np.savez_compressed(os.path.join(HERE, "sweeps.npz"), cloud0=clouds[0], cloud1=clouds[1], cloud2=clouds[2],
+                        cloud3=clouds[3], mat0=mats[0], mat2=mats[2], lags=np.asarray(lags), order=order, merged=out)
+    print("sweeps", out.shape, out.dtype, "order", order)
+
+
 def main():
     oracle.build(ref=True)
+    make_sweeps_golden()
     p2v = numba_points_to_voxel()
     cases = {
         # name: (cfg, generator, seed, num_points, max_points, max_voxels)

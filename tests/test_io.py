@@ -1,0 +1,58 @@
+"""CPU: the `.bin` reader / sweep merge (paddle3d_b200/io.py) against the golden produced by the
+reference's own LoadPointCloud.__call__ (tests/golden/make_golden.py: AST-extracted from reader.py:91-167)."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import golden
+from paddle3d_b200 import io as p3d_io
+
+
+def _write(tmp_path, g):
+    paths = []
+    for i in range(4):
+        p = os.path.join(tmp_path, "c%d.bin" % i)
+        g["cloud%d" % i].tofile(p)
+        paths.append(p)
+    mats = [g["mat0"], None, g["mat2"]]
+    sweeps = [p3d_io.Sweep(paths[i + 1], mats[i], float(g["lags"][i])) for i in range(3)]
+    return paths, sweeps
+
+
+def test_sweep_merge_matches_reference_bit_for_bit(tmp_path):
+    g = golden("sweeps.npz")
+    paths, sweeps = _write(str(tmp_path), g)
+    out = p3d_io.load_point_cloud(paths[0], 5, use_dim=[0, 1, 2, 4], use_time_lag=True, sweeps=sweeps,
+                                  sweep_remove_radius=1, order=g["order"])
+    assert out.dtype == np.float32 and out.shape == g["merged"].shape
+    assert np.array_equal(out, g["merged"])
+    # a different sweep order permutes blocks of rows, nothing else
+    other = p3d_io.load_point_cloud(paths[0], 5, use_dim=[0, 1, 2, 4], use_time_lag=True, sweeps=sweeps,
+                                    sweep_remove_radius=1)
+    assert other.shape == out.shape
+    key = lambda a: a[np.lexsort(a.T[::-1])]  # noqa: E731
+    assert np.array_equal(key(other), key(out))
+
+
+def test_reader_edge_cases(tmp_path):
+    g = golden("sweeps.npz")
+    paths, sweeps = _write(str(tmp_path), g)
+    k = p3d_io.read_bin(paths[0], 5, use_dim=4)
+    assert k.shape == (500, 4) and np.array_equal(k, g["cloud0"][:, :4])
+    plain = p3d_io.load_point_cloud(paths[0], 5)  # no sweeps, no lag: the file as it is
+    assert np.array_equal(plain, g["cloud0"])
+    lag = p3d_io.load_point_cloud(paths[0], 5, use_dim=[0, 1, 2, 3], use_time_lag=True)
+    assert lag.shape == (500, 5) and (lag[:, 4] == 0).all()
+    # every sweep point inside the removal square is dropped, the key frame keeps its own
+    far = p3d_io.load_point_cloud(paths[0], 5, use_dim=[0, 1, 2], sweeps=sweeps[1:2], sweep_remove_radius=100.0)
+    assert far.shape == (500, 3)
+    empty = os.path.join(str(tmp_path), "empty.bin")
+    np.zeros((0, 5), np.float32).tofile(empty)
+    assert p3d_io.load_point_cloud(empty, 5, use_dim=3).shape == (0, 3)
+    merged = p3d_io.load_point_cloud(empty, 5, use_dim=[0, 1, 2], sweeps=[p3d_io.Sweep(empty)], use_time_lag=True)
+    assert merged.shape == (0, 4)
+    with pytest.raises(ValueError):
+        p3d_io.load_point_cloud(paths[0], 5, sweeps=sweeps, order=[0, 0, 1])
+    with pytest.raises(ValueError):
+        p3d_io.read_bin(paths[0], 7)  # 2500 floats are not a multiple of 7
