@@ -185,14 +185,17 @@ def ncu_dram_bytes_per_frame():
     path = os.path.join(ROOT, "profiles", "r01_split_ncu_metrics.csv")
     if not os.path.exists(path):
         return None
-    rows = list(csv.reader(open(path)))
-    hdr, units = rows[0], rows[1]
-    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
-    total = 0.0
-    for name in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
-        i = hdr.index(name)
-        total += sum(float(r[i]) for r in rows[2:]) * scale[units[i]]
-    return total
+    try:
+        rows = list(csv.reader(open(path)))
+        hdr, units = rows[0], rows[1]
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+        total = 0.0
+        for name in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            i = hdr.index(name)
+            total += sum(float(r[i]) for r in rows[2:]) * scale[units[i]]
+        return total
+    except (ValueError, KeyError, IndexError, OSError):
+        return None  # a malformed capture must not take the benchmark down
 
 
 def main():
