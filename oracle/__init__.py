@@ -252,3 +252,42 @@ def bn_relu(x, gamma, beta, mean, var, eps, relu=True, residual=None):
     if relu:
         y = np.maximum(y, 0.0)
     return y.astype(np.float32)
+
+
+# --------------------------------------------------------------------------- dense 2-D convs (RPN / neck / head)
+def conv2d(x, weight, bias=None, stride=1, padding=0):
+    """x [B,Cin,H,W]; weight [Cout,Cin,kH,kW] (paddle.nn.Conv2D layout); fp64 accumulation."""
+    x, weight = _f(x), _f(weight)
+    b, cin, h, w = x.shape
+    cout, cin2, kh, kw = weight.shape
+    assert cin == cin2
+    oh, ow = (h + 2 * padding - kh) // stride + 1, (w + 2 * padding - kw) // stride + 1
+    out = np.empty((b, cout, oh, ow), np.float32)
+    bias = _f(bias) if bias is not None else None
+    lib().orc_conv2d_nchw(_fp(x), b, cin, h, w, _fp(weight), _fp(bias) if bias is not None else None, cout, kh, kw,
+                          int(stride), int(padding), _fp(out))
+    return out
+
+
+def deconv2d(x, weight, bias=None, stride=1):
+    """x [B,Cin,H,W]; weight [Cin,Cout,k,k] (paddle.nn.Conv2DTranspose layout), padding 0; fp64 accumulation."""
+    x, weight = _f(x), _f(weight)
+    b, cin, h, w = x.shape
+    cin2, cout, k, k2 = weight.shape
+    assert cin == cin2 and k == k2
+    oh, ow = (h - 1) * stride + k, (w - 1) * stride + k
+    out = np.empty((b, cout, oh, ow), np.float32)
+    bias = _f(bias) if bias is not None else None
+    lib().orc_deconv2d_nchw(_fp(x), b, cin, h, w, _fp(weight), _fp(bias) if bias is not None else None, cout, k,
+                            int(stride), _fp(out))
+    return out
+
+
+def bn2d_relu(x, gamma, beta, mean, var, eps, relu=True):
+    """paddle.nn.BatchNorm2D (eval) over axis 1 of an NCHW tensor + optional ReLU, fp64 internally."""
+    sh = (1, -1, 1, 1)
+    y = (x.astype(np.float64) - mean.reshape(sh)) / np.sqrt(var.astype(np.float64).reshape(sh) + eps)
+    y = y * gamma.reshape(sh) + beta.reshape(sh)
+    if relu:
+        y = np.maximum(y, 0.0)
+    return y.astype(np.float32)

@@ -101,3 +101,35 @@ def test_sparse_conv_oracle_vs_torch_dense(oracle_mod):
         got[oc[:, 0], :, oc[:, 1], oc[:, 2], oc[:, 3]] = of
         np.testing.assert_allclose(got, ref * act[:, None], rtol=1e-5, atol=1e-5)
         assert pairs > 0
+
+
+@pytest.mark.parametrize("cin,cout,k,stride,pad,bias", [(7, 5, 3, 1, 1, False), (6, 9, 3, 2, 1, True), (8, 4, 1, 1, 0, False)])
+def test_conv2d_oracle_vs_torch_fp64(oracle_mod, cin, cout, k, stride, pad, bias):
+    """Dense RPN/head conv restatement (PARITY UNPINNED by the reference: paddle.nn.Conv2D) against an independent
+    implementation: torch's CPU conv2d in fp64 on the same operands."""
+    import torch
+    rng = np.random.default_rng(cin * 100 + cout)
+    x = rng.normal(size=(2, cin, 13, 11)).astype(np.float32)
+    w = (rng.normal(size=(cout, cin, k, k)) * 0.2).astype(np.float32)
+    b = rng.normal(size=(cout,)).astype(np.float32) if bias else None
+    got = oracle_mod.conv2d(x, w, b, stride, pad)
+    want = torch.nn.functional.conv2d(torch.from_numpy(x).double(), torch.from_numpy(w).double(),
+                                      None if b is None else torch.from_numpy(b).double(), stride=stride, padding=pad)
+    assert got.shape == tuple(want.shape)
+    np.testing.assert_allclose(got, want.numpy(), rtol=1e-6, atol=1e-6)
+
+
+def test_deconv2d_and_bn2d_oracle_vs_torch_fp64(oracle_mod):
+    import torch
+    rng = np.random.default_rng(9)
+    x = rng.normal(size=(2, 6, 7, 5)).astype(np.float32)
+    w = (rng.normal(size=(6, 4, 2, 2)) * 0.3).astype(np.float32)  # [Cin, Cout, k, k]
+    got = oracle_mod.deconv2d(x, w, None, 2)
+    want = torch.nn.functional.conv_transpose2d(torch.from_numpy(x).double(), torch.from_numpy(w).double(), stride=2)
+    assert got.shape == (2, 4, 14, 10)
+    np.testing.assert_allclose(got, want.numpy(), rtol=1e-6, atol=1e-6)
+    g, bt, m, v = (rng.uniform(0.5, 1.5, 4), rng.normal(size=4), rng.normal(size=4), rng.uniform(0.5, 2.0, 4))
+    y = oracle_mod.bn2d_relu(got, g, bt, m, v, 1e-3)
+    ref = torch.nn.functional.batch_norm(want, torch.from_numpy(m), torch.from_numpy(v), torch.from_numpy(g),
+                                         torch.from_numpy(bt), False, 0.0, 1e-3).clamp_min(0)
+    np.testing.assert_allclose(y, ref.numpy(), rtol=1e-5, atol=1e-6)
