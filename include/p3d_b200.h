@@ -250,6 +250,26 @@ int p3d_sparse_conv_gather_gemm_split_tma(const float *in_split, int64_t n_in_ro
                                           const float *residual_split, int relu, float *out_f32, float *out_split,
                                           void *workspace, size_t workspace_bytes, p3d_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * EXPERIMENTAL (round-2 groundwork): dense 2-D convolution on tcgen05 for the RPN / neck /
+ * CenterHead (reference: backbones/second_backbone.py:72-120, necks/second_fpn.py:99-160,
+ * detection/centerpoint/center_head.py:43-220).  Images are "pixel split rows" [B*H*W][2][C] (the split-row format
+ * of the sparse layers with row = pixel).
+ *   p3d_nchw_to_pixel_split: fp32 [B, C, H, W] -> pixel split rows.
+ *   p3d_dense_conv2d_packed_weight_bytes / p3d_dense_conv2d_split: weights = per N tile (n_tile = 16 | 64 | 128 output
+ *     channels, zero-padded) the image p3d_sparse_conv_pack_weights makes of W[tap][Cin][n_tile], tiles concatenated.
+ *     up == 1: Conv2D(kh x kw, stride 1 | 2, zero padding pad); up > 1: Conv2DTranspose with kernel = stride = up
+ *     (pass kh = kw = stride = up, pad = 0).  Epilogue v * scale[c] + shift[c] (either may be NULL), optional ReLU.
+ *     Output: split rows of out_C channels written at column out_c0 (channel concat), and / or fp32 NCHW planes
+ *     [B, Cout, out_H, out_W].  Cin % 32 == 0; Cout % 16 == 0 for split-row output.
+ * ------------------------------------------------------------------------------------------- */
+int p3d_nchw_to_pixel_split(const float *in, int B, int C, int H, int W, float *out_split, p3d_stream_t stream);
+size_t p3d_dense_conv2d_packed_weight_bytes(int taps, int Cin, int Cout, int n_tile);
+int p3d_dense_conv2d_split(const float *in_split, int B, int H, int W, int Cin, const float *packed_weight, int Cout,
+                           int n_tile, int kh, int kw, int stride, int pad, int up, const float *scale,
+                           const float *shift, int relu, float *out_split, int out_C, int out_c0, float *out_nchw,
+                           p3d_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

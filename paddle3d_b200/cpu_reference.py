@@ -71,3 +71,36 @@ class CpuFrame:
             tc["nms_pre_max_size"], tc["nms_post_max_size"], True)
         t["postprocess"] = time.perf_counter() - t0
         return dict(bev=bev, boxes=boxes, scores=scores, labels=labels, times=t, num_voxels=k, pairs=list(self.pairs))
+
+
+class CpuDenseHead:
+    """CPU arm of the dense RPN / neck / head (dense_head.DenseRPNHead.export_numpy weights) through the oracle."""
+
+    def __init__(self, weights):
+        import oracle
+        self.o, self.w = oracle, weights
+
+    def _conv(self, l, x):
+        o = self.o
+        if l["up"] > 1:
+            y = o.deconv2d(x, l["weight"], l["bias"], l["up"])
+        else:
+            y = o.conv2d(x, l["weight"], l["bias"], l["stride"], l["padding"])
+        if l["bn"] is not None:
+            bn = l["bn"]
+            return o.bn2d_relu(y, bn["gamma"], bn["beta"], bn["mean"], bn["var"], bn["eps"], relu=l["relu"])
+        return np.maximum(y, 0.0) if l["relu"] else y
+
+    def run(self, bev):
+        w, x, feats = self.w, bev, []
+        for blk in w["blocks"]:
+            for l in blk:
+                x = self._conv(l, x)
+            feats.append(x)
+        cat = np.concatenate([self._conv(l, f) for l, f in zip(w["deblocks"], feats)], axis=1)
+        s = self._conv(w["shared"], cat)
+        out = {}
+        for hs in w["heads"]:
+            for name, a, fin in hs:
+                out.setdefault(name, []).append(self._conv(fin, self._conv(a, s)))
+        return out

@@ -1,0 +1,82 @@
+"""EXPERIMENTAL: dense 2-D convolutions of the RPN / neck / CenterHead on tcgen05
+(`csrc/dense_conv_tc.cu`).  Images travel as "pixel split rows" [B*H*W, 2*C] fp32 (hi half of all channels, then lo
+half) between layers; weights are given in Paddle's layouts (Conv2D [Cout, Cin, kH, kW], Conv2DTranspose
+[Cin, Cout, k, k]).  Written in round 1 without GPU time left to run it: not on any default path."""
+import torch
+
+from .._lib import check, lib
+from .._mem import ptr, require_cuda, stream
+
+
+def n_tile_for(cout):
+    """Output-channel tile of the kernel: 128 for wide layers, 64, or 16 for the 1-3 channel head outputs."""
+    return 128 if cout >= 128 else (64 if cout > 16 else 16)
+
+
+def nchw_to_pixel_split(x):
+    x = require_cuda(x, "x", torch.float32)
+    b, c, h, w = x.shape
+    out = torch.empty((b * h * w, 2 * c), dtype=torch.float32, device=x.device)
+    check(lib().p3d_nchw_to_pixel_split(ptr(x), b, c, h, w, ptr(out), stream(x.device)), "nchw_to_pixel_split")
+    return out
+
+
+def _pack(w_tci, n_tile):
+    """w_tci [taps, Cin, Cout] fp32 on the device -> per-N-tile packed images, concatenated."""
+    L = lib()
+    taps, cin, cout = w_tci.shape
+    tiles = (cout + n_tile - 1) // n_tile
+    total = L.p3d_dense_conv2d_packed_weight_bytes(taps, cin, cout, n_tile)
+    if not total:
+        raise ValueError("unsupported dense conv shape: taps %d Cin %d Cout %d" % (taps, cin, cout))
+    packed = torch.zeros((total // 4,), dtype=torch.float32, device=w_tci.device)
+    padded = torch.zeros((taps, cin, tiles * n_tile), dtype=torch.float32, device=w_tci.device)
+    padded[:, :, :cout] = w_tci
+    block = taps * cin * 2 * n_tile
+    for t in range(tiles):
+        wt = padded[:, :, t * n_tile:(t + 1) * n_tile].contiguous()
+        dst = packed[t * block:(t + 1) * block]
+        check(L.p3d_sparse_conv_pack_weights(ptr(wt), taps, cin, n_tile, ptr(dst), stream(wt.device)),
+              "sparse_conv_pack_weights")
+    return packed
+
+
+def pack_conv_weight(weight, n_tile):
+    """paddle.nn.Conv2D weight [Cout, Cin, kH, kW] -> packed (tap = dy * kW + dx)."""
+    weight = require_cuda(weight, "weight", torch.float32)
+    cout, cin, kh, kw = weight.shape
+    return _pack(weight.permute(2, 3, 1, 0).reshape(kh * kw, cin, cout).contiguous(), n_tile)
+
+
+def pack_deconv_weight(weight, n_tile):
+    """paddle.nn.Conv2DTranspose weight [Cin, Cout, k, k] -> packed (tap = dy * k + dx)."""
+    weight = require_cuda(weight, "weight", torch.float32)
+    cin, cout, k, k2 = weight.shape
+    return _pack(weight.permute(2, 3, 0, 1).reshape(k * k2, cin, cout).contiguous(), n_tile)
+
+
+def dense_conv2d(x_split, shape, packed, cout, n_tile, kernel, stride=1, padding=0, up=1, scale=None, shift=None,
+                 relu=False, out_split=None, out_channels=None, out_c0=0, want_nchw=False):
+    """x_split [B*H*W, 2*Cin]; shape = (B, H, W, Cin).  Returns (out_split or None, out_nchw or None, (B, oH, oW)).
+
+    out_split: an existing [B*oH*oW, 2*out_channels] buffer to write columns [out_c0, out_c0 + cout) of (channel
+    concat), or None to allocate one of `out_channels` (default cout) channels; want_nchw adds fp32 planes."""
+    x_split = require_cuda(x_split, "x_split", torch.float32)
+    b, h, w, cin = [int(v) for v in shape]
+    if up > 1:
+        oh, ow = h * up, w * up
+        kh = kw = st = up
+        pd = 0
+    else:
+        kh = kw = int(kernel)
+        st, pd = int(stride), int(padding)
+        oh, ow = (h + 2 * pd - kh) // st + 1, (w + 2 * pd - kw) // st + 1
+    dev = x_split.device
+    oc = int(out_channels or cout)
+    if out_split is None and not want_nchw:
+        out_split = torch.empty((b * oh * ow, 2 * oc), dtype=torch.float32, device=dev)
+    out_nchw = torch.empty((b, cout, oh, ow), dtype=torch.float32, device=dev) if want_nchw else None
+    check(lib().p3d_dense_conv2d_split(ptr(x_split), b, h, w, cin, ptr(packed), int(cout), int(n_tile), kh, kw, st, pd,
+                                       int(up), ptr(scale), ptr(shift), int(relu), ptr(out_split), oc, int(out_c0),
+                                       ptr(out_nchw), stream(dev)), "dense_conv2d_split")
+    return out_split, out_nchw, (b, oh, ow)

@@ -1,0 +1,80 @@
+"""GPU parity of the EXPERIMENTAL dense 2-D conv path (RPN / neck / CenterHead) against the oracle's
+fp64-accumulating conv2d / deconv2d.  The kernels were written at the end of round 1 without GPU time left to run
+them, so these tests only run with P3D_EXPERIMENTAL=1 until they have been seen green."""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("P3D_EXPERIMENTAL") != "1", reason="experimental (P3D_EXPERIMENTAL=1)")]
+
+
+def _t(cuda, a):
+    import torch
+    return torch.from_numpy(np.ascontiguousarray(a)).to(cuda)
+
+
+def _merge(split, b, h, w, c):
+    """pixel split rows [B*H*W, 2C] -> fp32 NCHW (hi + lo)."""
+    s = split.cpu().numpy().reshape(b, h, w, 2, c)
+    return (s[:, :, :, 0, :] + s[:, :, :, 1, :]).transpose(0, 3, 1, 2)
+
+
+def test_nchw_to_pixel_split(cuda):
+    from paddle3d_b200.ops import dense_conv as dc
+    rng = np.random.default_rng(0)
+    x = rng.normal(size=(2, 37, 9, 13)).astype(np.float32)
+    s = dc.nchw_to_pixel_split(_t(cuda, x)).cpu().numpy().reshape(2, 9, 13, 2, 37)
+    hi, lo = s[..., 0, :], s[..., 1, :]
+    assert np.array_equal((hi.view(np.uint32) & 0x1fff), np.zeros_like(hi, np.uint32))  # tf32: 13 low bits clear
+    np.testing.assert_allclose((hi + lo).transpose(0, 3, 1, 2), x, rtol=3e-7, atol=0)
+
+
+@pytest.mark.parametrize("cin,cout,k,stride,pad,up,h,w", [
+    (32, 64, 3, 1, 1, 1, 20, 23),     # 3x3, ragged tiles on both axes
+    (64, 128, 3, 2, 1, 1, 21, 34),    # stride 2 (tensor-map element stride), odd input height
+    (128, 256, 1, 1, 0, 1, 16, 16),   # 1x1, two N tiles of 128
+    (64, 64, 2, 2, 0, 2, 9, 11),      # transposed conv k = s = 2
+    (64, 3, 3, 1, 1, 1, 17, 19),      # head output: N tile 16, fp32 NCHW planes
+    (512, 64, 3, 1, 1, 1, 12, 18),    # the shared conv's channel count (16 uses per tap)
+])
+def test_dense_conv_vs_oracle(cuda, oracle_mod, cin, cout, k, stride, pad, up, h, w):
+    import torch
+    from paddle3d_b200.ops import dense_conv as dc
+    rng = np.random.default_rng(cin + cout)
+    x = rng.normal(size=(2, cin, h, w)).astype(np.float32)
+    wshape = (cin, cout, k, k) if up > 1 else (cout, cin, k, k)
+    wt = (rng.normal(size=wshape) / np.sqrt(cin * k * k)).astype(np.float32)
+    scale = rng.uniform(0.5, 1.5, cout).astype(np.float32)
+    shift = rng.normal(size=cout).astype(np.float32)
+    ref = (oracle_mod.deconv2d(x, wt, None, up) if up > 1 else oracle_mod.conv2d(x, wt, None, stride, pad)).astype(np.float64)
+    ref = np.maximum(ref * scale.reshape(1, -1, 1, 1) + shift.reshape(1, -1, 1, 1), 0.0)
+    nt = dc.n_tile_for(cout)
+    packed = (dc.pack_deconv_weight if up > 1 else dc.pack_conv_weight)(_t(cuda, wt), nt)
+    xs = dc.nchw_to_pixel_split(_t(cuda, x))
+    want_nchw = cout % 16 != 0
+    o_split, o_nchw, (b, oh, ow) = dc.dense_conv2d(xs, (2, h, w, cin), packed, cout, nt, k, stride, pad, up, _t(cuda, scale),
+                                                   _t(cuda, shift), True, want_nchw=want_nchw)
+    torch.cuda.synchronize()
+    got = o_nchw.cpu().numpy() if want_nchw else _merge(o_split, b, oh, ow, cout)
+    assert got.shape == ref.shape
+    assert np.abs(got - ref).max() <= 1e-4 * max(1.0, np.abs(ref).max())
+
+
+def test_concat_offset_and_small_head(cuda, oracle_mod):
+    import torch
+    from paddle3d_b200.cpu_reference import CpuDenseHead
+    from paddle3d_b200.dense_head import DenseRPNHead
+    net = DenseRPNHead(in_channels=64, out_channels=(32, 64), layer_nums=(1, 2), downsample_strides=(1, 2),
+                       fpn_out_channels=(64, 64), upsample_strides=(1, 2), tasks=(1, 2), share_conv_channel=64)
+    net.init_weight(seed=2, device=cuda, randomize_bn=True)
+    rng = np.random.default_rng(1)
+    bev = rng.normal(size=(1, 64, 40, 36)).astype(np.float32)
+    got = net(_t(cuda, bev))
+    torch.cuda.synchronize()
+    want = CpuDenseHead(net.export_numpy()).run(bev)
+    for name in want:
+        for g, w in zip(got[name], want[name]):
+            assert tuple(g.shape) == w.shape
+            assert np.abs(g.cpu().numpy() - w).max() <= 1e-4 * max(1.0, np.abs(w).max()), name

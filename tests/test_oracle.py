@@ -133,3 +133,46 @@ def test_deconv2d_and_bn2d_oracle_vs_torch_fp64(oracle_mod):
     ref = torch.nn.functional.batch_norm(want, torch.from_numpy(m), torch.from_numpy(v), torch.from_numpy(g),
                                          torch.from_numpy(bt), False, 0.0, 1e-3).clamp_min(0)
     np.testing.assert_allclose(y, ref.numpy(), rtol=1e-5, atol=1e-6)
+
+
+def test_cpu_dense_head_vs_torch_fp64(oracle_mod):
+    """Structure of the dense RPN / neck / head restatement (dense_head.DenseRPNHead + cpu_reference.CpuDenseHead:
+    block order, stride-2 stage, 1x1 / transposed-conv neck, channel concat order, shared conv, per-task heads)
+    against the same network written with torch's fp64 CPU ops."""
+    import torch
+    import torch.nn.functional as F
+    from paddle3d_b200.cpu_reference import CpuDenseHead
+    from paddle3d_b200.dense_head import DenseRPNHead
+    net = DenseRPNHead(in_channels=32, out_channels=(32, 64), layer_nums=(1, 2), downsample_strides=(1, 2),
+                       fpn_out_channels=(32, 32), upsample_strides=(1, 2), tasks=(1, 2), share_conv_channel=32)
+    net.init_weight(seed=4, device=None, randomize_bn=True)
+    w = net.export_numpy()
+    rng = np.random.default_rng(0)
+    bev = rng.normal(size=(1, 32, 20, 28)).astype(np.float32)
+    got = CpuDenseHead(w).run(bev)
+
+    def conv(l, x):
+        wt = torch.from_numpy(l["weight"]).double()
+        b = None if l["bias"] is None else torch.from_numpy(l["bias"]).double()
+        y = (F.conv_transpose2d(x, wt, b, stride=l["up"]) if l["up"] > 1
+             else F.conv2d(x, wt, b, stride=l["stride"], padding=l["padding"]))
+        if l["bn"] is not None:
+            bn = {k: torch.from_numpy(np.asarray(v)).double() for k, v in l["bn"].items() if k != "eps"}
+            y = F.batch_norm(y, bn["mean"], bn["var"], bn["gamma"], bn["beta"], False, 0.0, l["bn"]["eps"])
+        return y.clamp_min(0) if l["relu"] else y
+
+    x, feats = torch.from_numpy(bev).double(), []
+    for blk in w["blocks"]:
+        for l in blk:
+            x = conv(l, x)
+        feats.append(x)
+    cat = torch.cat([conv(l, f) for l, f in zip(w["deblocks"], feats)], 1)
+    assert cat.shape == (1, 64, 20, 28)
+    s = conv(w["shared"], cat)
+    for ti, hs in enumerate(w["heads"]):
+        for name, a, fin in hs:
+            want = conv(fin, conv(a, s)).numpy()
+            g = got[name][ti]
+            assert g.shape == want.shape
+            np.testing.assert_allclose(g, want, rtol=2e-5, atol=2e-5)
+    assert got["hm"][1].shape == (1, 2, 20, 28) and got["reg"][0].shape == (1, 2, 20, 28)
