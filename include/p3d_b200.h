@@ -251,7 +251,7 @@ int p3d_sparse_conv_gather_gemm_split_tma(const float *in_split, int64_t n_in_ro
                                           void *workspace, size_t workspace_bytes, p3d_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
- * EXPERIMENTAL (round-2 groundwork): dense 2-D convolution on tcgen05 for the RPN / neck /
+ * SURVEY.md 8f-1 (parity-green, performance not measured yet): dense 2-D convolution on tcgen05 for the RPN / neck /
  * CenterHead (reference: backbones/second_backbone.py:72-120, necks/second_fpn.py:99-160,
  * detection/centerpoint/center_head.py:43-220).  Images are "pixel split rows" [B*H*W][2][C] (the split-row format
  * of the sparse layers with row = pixel).

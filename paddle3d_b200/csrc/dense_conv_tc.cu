@@ -1,7 +1,7 @@
 // Dense 2-D convolution on tcgen05 for the RPN / neck / CenterHead row (reference:
 // backbones/second_backbone.py:72-120, necks/second_fpn.py:99-160, detection/centerpoint/center_head.py:43-220).
-// EXPERIMENTAL: written in round 1 without GPU time left to run it; not on any default path, tests behind
-// P3D_EXPERIMENTAL=1.
+// Parity-green on a B200 (tests/test_gpu_dense.py) at the end of round 1; performance not measured yet, not on the
+// default bench path.
 //
 // The image is kept as "pixel split rows" [B*H*W][2][C] (NHWC with the tf32 hi half of all channels, then the lo half —
 // the row format of the sparse-conv layers with row = pixel), so a 3x3 tap of 32 input channels for a 16 x 8 pixel

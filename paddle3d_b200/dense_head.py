@@ -1,8 +1,9 @@
-"""EXPERIMENTAL: the dense part of CenterPoint between the BEV tensor and the postprocess —
+"""the dense part of CenterPoint between the BEV tensor and the postprocess —
 SecondBackbone (backbones/second_backbone.py:72-120), SecondFPN (necks/second_fpn.py:99-160, use_conv_for_no_stride)
 and CenterHead (detection/centerpoint/center_head.py:43-220) — as a chain of `ops.dense_conv.dense_conv2d` launches
 with BatchNorm folded into the conv epilogue.  Same constructor vocabulary as the reference's yml
-(configs/centerpoint/centerpoint_voxels_0075voxel_nuscenes_10sweep.yml:127-162).  Not on any default path yet."""
+(configs/centerpoint/centerpoint_voxels_0075voxel_nuscenes_10sweep.yml:127-162).  Parity-green against the CPU
+reference (tests/test_gpu_dense.py); not part of the default bench frame yet."""
 import numpy as np
 import torch
 

@@ -1,7 +1,7 @@
-"""EXPERIMENTAL: dense 2-D convolutions of the RPN / neck / CenterHead on tcgen05
+"""dense 2-D convolutions of the RPN / neck / CenterHead on tcgen05
 (`csrc/dense_conv_tc.cu`).  Images travel as "pixel split rows" [B*H*W, 2*C] fp32 (hi half of all channels, then lo
 half) between layers; weights are given in Paddle's layouts (Conv2D [Cout, Cin, kH, kW], Conv2DTranspose
-[Cin, Cout, k, k]).  Written in round 1 without GPU time left to run it: not on any default path."""
+[Cin, Cout, k, k]).  Parity-green on a B200 (tests/test_gpu_dense.py); performance not measured yet."""
 import torch
 
 from .._lib import check, lib
