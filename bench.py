@@ -206,6 +206,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--precision", default="tf32x3_split", choices=["fp32", "tf32x3", "tf32x3_split", "tf32x3_tma"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--with-head", action="store_true",
+                    help="also run the dense RPN/neck/CenterHead (SURVEY 8f-1) and postprocess ITS outputs; not the "
+                         "default workload (parity-green, not tuned)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
@@ -233,7 +236,7 @@ def main():
     cfg = synth.C3
     precision = {"tf32x3": sp.TF32X3, "tf32x3_split": sp.TF32X3_SPLIT, "tf32x3_tma": sp.TF32X3_TMA, "fp32": sp.FP32}[args.precision]
     caps = [int(x) for x in os.environ["P3D_LEVEL_CAPS"].split(",")] if os.environ.get("P3D_LEVEL_CAPS") else None
-    pipe = CenterPointHotPath(cfg, dev, precision=precision, seed=0, level_caps=caps)
+    pipe = CenterPointHotPath(cfg, dev, precision=precision, seed=0, level_caps=caps, with_head=args.with_head)
     if world > 1:  # weights only: one broadcast over NVLink at start, no per-frame collective
         from paddle3d_b200.sharding import broadcast_weights
         broadcast_weights(pipe.net, 0)
@@ -409,7 +412,10 @@ def main():
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32" if precision == sp.FP32 else "tf32x3(f32 accum)",
-                "data": "synthetic", "config": {"workload": WORKLOAD, "frames_in_pool": POOL,
+                "data": "synthetic", "config": {"workload": WORKLOAD if not args.with_head else WORKLOAD.replace(
+                    "synthetic head tensors); dense 2-D RPN/head (SURVEY §8f-1) not included",
+                    "head tensors computed by the dense RPN/neck/CenterHead on tcgen05: --with-head, not the default "
+                    "workload); cpu_baseline is for the default workload"), "frames_in_pool": POOL,
                                                 "l2": "input pool 192 MB > 126 MB L2; no explicit flush",
                                                 "parallelism": "frame-parallel x%d (replicas, NCCL weight broadcast only)" % world,
                                                 "precision": args.precision},

@@ -22,7 +22,7 @@ from .ops import voxelize as vox
 
 class CenterPointHotPath:
     def __init__(self, cfg=None, device="cuda:0", precision=sp.FP32, seed=0, num_points=None, level_caps=None,
-                 head_seed=0):
+                 head_seed=0, with_head=False):
         self.cfg = dict(cfg or synth.C3)
         self.device = torch.device(device)
         self.n = int(num_points or self.cfg["num_points"])
@@ -36,6 +36,13 @@ class CenterPointHotPath:
         h = synth.centerpoint_head_outputs(head_seed)
         self.head_host = h
         self.head = {k: [torch.from_numpy(x).to(self.device) for x in v] for k, v in h.items()}
+        # with_head: run the dense RPN / neck / CenterHead (dense_head.DenseRPNHead) on the BEV tensor and
+        # feed ITS outputs to the postprocess instead of the resident synthetic head tensors (parity-green per layer and
+        # as a small network; this whole-frame composition has not been timed yet, hence off by default)
+        self.dense = None
+        if with_head:
+            from .dense_head import DenseRPNHead
+            self.dense = DenseRPNHead(in_channels=128 * 2).init_weight(seed=seed + 1, device=self.device)
         self.points = torch.zeros((self.n, self.F), dtype=torch.float32, device=self.device)  # static input
         self.graph = None
         self.out = None
@@ -52,7 +59,7 @@ class CenterPointHotPath:
         mean, coors, npv, nv = vox.voxelize_mean(self.points, cfg["voxel_size"], cfg["point_cloud_range"],
                                                  cfg["max_points"], cfg["max_voxels"], 0)
         bev = self.net(mean, coors, 1, num=nv)
-        h = self.head
+        h = self.dense(bev) if self.dense is not None else self.head
         boxes, scores, labels, counts = cpp.centerpoint_postprocess_device(
             h["hm"], h["reg"], h["height"], h["dim"], h["vel"], h["rot"], cfg["voxel_size"][:2],
             cfg["point_cloud_range"], tc["post_center_limit_range"], self.label_off, tc["down_ratio"],

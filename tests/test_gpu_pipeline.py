@@ -75,3 +75,23 @@ def test_graph_sweep_and_side_stream_agree_with_eager(cuda):
     side.capture()
     b, s, l = side.infer(pinned[1])
     assert torch.equal(b, want[1][0]) and torch.equal(side.out["bev"], want[1][3])
+
+
+@pytest.mark.skipif(__import__("os").environ.get("P3D_EXPERIMENTAL") != "1", reason="composition not run on a GPU yet")
+def test_frame_with_dense_head(cuda, oracle_mod):
+    """with_head=True: BEV -> DenseRPNHead -> postprocess.  The head tensors must match the CPU reference run on the
+    GPU's own BEV tensor (the per-layer and small-network parity is in test_gpu_dense.py); boxes are not compared bit
+    for bit because candidates within 1e-4 of the score threshold may flip."""
+    import torch
+    from paddle3d_b200.cpu_reference import CpuDenseHead
+    pipe = _pipe(cuda, 2, with_head=True)
+    pipe.points.copy_(torch.from_numpy(_frames(1)[0]).to(cuda))
+    with torch.cuda.stream(pipe.stream):
+        out = pipe.forward_device()
+        heads = pipe.dense(out["bev"])
+    pipe.stream.synchronize()
+    want = CpuDenseHead(pipe.dense.export_numpy()).run(out["bev"].cpu().numpy())
+    for name in want:
+        for g, w in zip(heads[name], want[name]):
+            assert np.abs(g.cpu().numpy() - w).max() <= 1e-4 * max(1.0, np.abs(w).max()), name
+    assert int(out["counts"][-1].item()) >= len(pipe.label_off)  # at least the one row per task the op always emits
