@@ -270,6 +270,14 @@ int p3d_dense_conv2d_split(const float *in_split, int B, int H, int W, int Cin, 
                            const float *shift, int relu, float *out_split, int out_C, int out_c0, float *out_nchw,
                            p3d_stream_t stream);
 
+/* EXPERIMENTAL (never run on a GPU yet): the grouped 3x3 output convs of CenterHead's SeparateHeads
+ * (center_head.py:80-117) as one CUDA-core launch.  in_split: pixel split rows [B*H*W][2][in_C]; group g convolves
+ * channels [g*Cin, (g+1)*Cin) with weight [groups][9][Cin][4] (outputs zero-padded to 4) + bias [groups][4] and
+ * writes cnt[g] fp32 planes from plane0[g] of out_nchw [B, planes, H, W] (plane0 / cnt are HOST arrays). */
+int p3d_head_final_conv(const float *in_split, int B, int H, int W, int in_C, int Cin, int groups, const float *weight,
+                        const float *bias, const int32_t *plane0_host, const int32_t *cnt_host, int planes,
+                        float *out_nchw, p3d_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

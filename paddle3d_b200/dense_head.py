@@ -137,3 +137,73 @@ class DenseRPNHead:
         return out
 
     __call__ = forward
+
+    # ---- EXPERIMENTAL (never run on a GPU yet): the 36 + 36 head convs as two launches
+    def _batched_params(self, device):
+        """One Conv(64 -> 36 * 64) with the 36 ConvModules' weights / folded BN concatenated along Cout, and the final
+        convs' weights as [groups][9][Cin][4] for p3d_head_final_conv."""
+        if getattr(self, "_batched", None) is not None:
+            return self._batched
+        firsts = [a for hs in self.heads for _, a, _ in hs]
+        finals = [(n, f) for hs in self.heads for n, _, f in hs]
+        cin = firsts[0].cin
+        big = _Conv(cin, sum(a.cout for a in firsts), 3, 1, 1, bias=True, bn_eps=firsts[0].bn_eps)
+        w = np.concatenate([a.np["weight"] for a in firsts], 0)
+        scale, shift = [], []
+        for a in firsts:  # same folding as _Conv.init
+            bn = a.np["bn"]
+            s_ = bn["gamma"].astype(np.float64) / np.sqrt(bn["var"].astype(np.float64) + bn["eps"])
+            scale.append(s_)
+            shift.append((a.np["bias"].astype(np.float64) - bn["mean"]) * s_ + bn["beta"])
+        big.dev = dict(packed=dc.pack_conv_weight(torch.from_numpy(w).to(device), big.n_tile),
+                       scale=torch.from_numpy(np.concatenate(scale).astype(np.float32)).to(device),
+                       shift=torch.from_numpy(np.concatenate(shift).astype(np.float32)).to(device))
+        groups = len(finals)
+        fw = np.zeros((groups, 9, cin, 4), np.float32)
+        fb = np.zeros((groups, 4), np.float32)
+        plane0, cnt, p0 = [], [], 0
+        for g, (_, f) in enumerate(finals):
+            k = f.cout
+            fw[g, :, :, :k] = f.np["weight"].transpose(2, 3, 1, 0).reshape(9, cin, k)  # [k, cin, 3, 3] -> [tap][cin][k]
+            fb[g, :k] = f.np["bias"]
+            plane0.append(p0)
+            cnt.append(k)
+            p0 += k
+        self._batched = dict(big=big, fw=torch.from_numpy(fw).to(device), fb=torch.from_numpy(fb).to(device),
+                             plane0=np.asarray(plane0, np.int32), cnt=np.asarray(cnt, np.int32), planes=p0,
+                             names=[n for n, _ in finals])
+        return self._batched
+
+    def forward_batched(self, bev):
+        """Same result as forward(); the 36 ConvModules run as one 64 -> 2304 conv and the 36 output convs as one
+        grouped CUDA-core launch (p3d_head_final_conv)."""
+        from ._lib import check, lib
+        from ._mem import ptr, stream
+        b, c, h, w = bev.shape
+        x, shape = dc.nchw_to_pixel_split(bev), (b, h, w, c)
+        feats = []
+        for blk in self.blocks:
+            for conv in blk:
+                x, _, (b_, oh, ow) = conv(x, shape)
+                shape = (b_, oh, ow, conv.cout)
+            feats.append((x, shape))
+        cat, c0, out_hw = None, 0, None
+        for (f, fshape), de in zip(feats, self.deblocks):
+            if cat is None:
+                out_hw = (fshape[1] * de.up, fshape[2] * de.up)
+                cat = torch.empty((fshape[0] * out_hw[0] * out_hw[1], 2 * self.fpn_channels), dtype=torch.float32, device=bev.device)
+            de(f, fshape, out_split=cat, out_channels=self.fpn_channels, out_c0=c0)
+            c0 += de.cout
+        H, W = out_hw
+        s, _, _ = self.shared(cat, (b, H, W, self.fpn_channels))
+        bp = self._batched_params(bev.device)
+        big = bp["big"]
+        mid, _, _ = big(s, (b, H, W, self.shared.cout))  # [B*H*W][2][36 * 64]
+        planes = torch.empty((b, bp["planes"], H, W), dtype=torch.float32, device=bev.device)
+        check(lib().p3d_head_final_conv(ptr(mid), b, H, W, big.cout, self.shared.cout, len(bp["cnt"]), ptr(bp["fw"]),
+                                        ptr(bp["fb"]), bp["plane0"].ctypes.data, bp["cnt"].ctypes.data, bp["planes"],
+                                        ptr(planes), stream(bev.device)), "head_final_conv")
+        out = {}
+        for name, p0, k in zip(bp["names"], bp["plane0"], bp["cnt"]):
+            out.setdefault(name, []).append(planes[:, int(p0):int(p0) + int(k)])
+        return out

@@ -76,3 +76,27 @@ def test_concat_offset_and_small_head(cuda, oracle_mod):
         for g, w in zip(got[name], want[name]):
             assert tuple(g.shape) == w.shape
             assert np.abs(g.cpu().numpy() - w).max() <= 1e-4 * max(1.0, np.abs(w).max()), name
+
+
+@pytest.mark.skipif(__import__("os").environ.get("P3D_EXPERIMENTAL") != "1", reason="never run on a GPU yet")
+def test_batched_head_matches_per_layer_head(cuda, oracle_mod):
+    """forward_batched (one 64 -> 36*64 conv + one grouped CUDA-core launch for the output convs) against forward()
+    and the CPU reference."""
+    import torch
+    from paddle3d_b200.cpu_reference import CpuDenseHead
+    from paddle3d_b200.dense_head import DenseRPNHead
+    net = DenseRPNHead(in_channels=64, out_channels=(32, 64), layer_nums=(1, 1), downsample_strides=(1, 2),
+                       fpn_out_channels=(64, 64), upsample_strides=(1, 2), tasks=(1, 2, 2), share_conv_channel=64)
+    net.init_weight(seed=6, device=cuda, randomize_bn=True)
+    rng = np.random.default_rng(3)
+    bev = rng.normal(size=(1, 64, 24, 40)).astype(np.float32)
+    a = net(_t(cuda, bev))
+    b = net.forward_batched(_t(cuda, bev))
+    torch.cuda.synchronize()
+    want = CpuDenseHead(net.export_numpy()).run(bev)
+    for name in want:
+        for x, y, w in zip(a[name], b[name], want[name]):
+            tol = 1e-4 * max(1.0, np.abs(w).max())
+            assert tuple(y.shape) == w.shape
+            assert np.abs(y.cpu().numpy() - w).max() <= tol, name
+            assert np.abs(y.cpu().numpy() - x.cpu().numpy()).max() <= tol, name
