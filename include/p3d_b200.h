@@ -278,6 +278,16 @@ int p3d_head_final_conv(const float *in_split, int B, int H, int W, int in_C, in
                         const float *bias, const int32_t *plane0_host, const int32_t *cnt_host, int planes,
                         float *out_nchw, p3d_stream_t stream);
 
+/* EXPERIMENTAL (never run on a GPU yet), SURVEY.md 8f-2: PillarFeatureNet with one PFNLayer
+ * (models/voxel_encoders/pillar_encoder.py:156-210, :81-106) fused into one launch: voxels [n, M, F] + counts + coors
+ * [n, 4] (b, z, y, x) -> pillar features [n, C].  weight [F + 5, C] (paddle.nn.Linear layout, no bias); BatchNorm1D
+ * folded by the caller: y = x * bn_scale[c] + bn_shift[c].  Rows >= *num_voxels_dev (if given) are left untouched. */
+int p3d_pillar_feature_net(const float *voxels, const int32_t *num_points_per_voxel, const int32_t *coors,
+                           const int32_t *num_voxels_dev, int64_t n_cap, int max_points, int num_point_dim,
+                           int out_channels, const float *weight, const float *bn_scale, const float *bn_shift,
+                           const float *voxel_size_host, const float *point_cloud_range_host, float *out,
+                           p3d_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

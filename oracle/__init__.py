@@ -291,3 +291,29 @@ def bn2d_relu(x, gamma, beta, mean, var, eps, relu=True):
     if relu:
         y = np.maximum(y, 0.0)
     return y.astype(np.float32)
+
+
+# --------------------------------------------------------------------------- PillarFeatureNet (PointPillars encoder)
+def pillar_feature_net(voxels, npv, coors, weight, gamma, beta, mean, var, eps, voxel_size, point_cloud_range):
+    """PillarFeatureNet with one (last) PFNLayer, `legacy` flag irrelevant (PARITY UNPINNED: paddle ops; restated from
+    models/voxel_encoders/pillar_encoder.py:156-210 and :81-106).  voxels [N, M, F] (x, y, z, ...), npv [N], coors [N, 4]
+    (b, z, y, x); weight [F + 5, C] (paddle.nn.Linear layout, no bias).  Decoration: xyz - mean of the pillar's points,
+    xy - pillar centre (coors[:, 3] * vx + vx / 2 + x_min, coors[:, 2] * vy + vy / 2 + y_min); rows >= npv are zeroed
+    AFTER the decoration (:193-198) and still take part in the max (their value is ReLU(BN(0))).  fp64 internally.
+    Paddle's basic slicing copies, so the in-place edit of `f_center` (:181-187) does not alias `features`."""
+    v = np.asarray(voxels, np.float64)
+    n, m, f = v.shape
+    cnt = np.asarray(npv, np.float64).reshape(-1, 1, 1)
+    pmean = v[:, :, :3].sum(1, keepdims=True) / cnt
+    f_cluster = v[:, :, :3] - pmean
+    vx, vy = float(voxel_size[0]), float(voxel_size[1])
+    xo, yo = vx / 2 + float(point_cloud_range[0]), vy / 2 + float(point_cloud_range[1])
+    c = np.asarray(coors)
+    f_center = np.stack([v[:, :, 0] - (c[:, 3].reshape(-1, 1).astype(np.float32).astype(np.float64) * np.float32(vx) + np.float32(xo)),
+                         v[:, :, 1] - (c[:, 2].reshape(-1, 1).astype(np.float32).astype(np.float64) * np.float32(vy) + np.float32(yo))], -1)
+    feats = np.concatenate([v, f_cluster, f_center], -1)
+    mask = (np.arange(m).reshape(1, -1) < np.asarray(npv).reshape(-1, 1)).astype(np.float64)
+    feats = feats * mask[:, :, None]
+    x = feats @ np.asarray(weight, np.float64)
+    x = (x - mean) / np.sqrt(np.asarray(var, np.float64) + eps) * gamma + beta
+    return np.maximum(x, 0.0).max(1).astype(np.float32)

@@ -142,3 +142,26 @@ def test_pillar_scatter(cuda, oracle_mod, cfg, C):
     got2 = layer(torch.from_numpy(feats).to(cuda), torch.from_numpy(coors2).to(cuda), 2, num=num).cpu().numpy()
     want2 = oracle_mod.pillar_scatter(feats[:k - 5], coors2[:k - 5], 2, layer.ny, layer.nx)
     assert np.array_equal(got2, want2)
+
+
+@pytest.mark.skipif(__import__("os").environ.get("P3D_EXPERIMENTAL") != "1", reason="never run on a GPU yet")
+def test_pillar_feature_net(cuda, oracle_mod):
+    """hard_voxelize (C2 geometry) -> PillarFeatureNet against the oracle restatement; 1e-4 relative."""
+    import torch
+    from paddle3d_b200.ops import pillar_encoder, voxelize
+    cfg = synth.C2
+    pts = synth.lidar_cloud(cfg, 4, num_points=6000)
+    P, V = 32, 3000
+    vox, co, npv, nv = voxelize.hard_voxelize(torch.from_numpy(pts).to(cuda), cfg["voxel_size"], cfg["point_cloud_range"], P, V)
+    k = int(nv[0].item())
+    coors = torch.cat([torch.zeros((V, 1), dtype=torch.int32, device=cuda), co], 1).contiguous()
+    rng = np.random.default_rng(8)
+    f, c = pts.shape[1], 64
+    w = (rng.normal(size=(f + 5, c)) * 0.3).astype(np.float32)
+    g, b, mu, var = rng.uniform(0.5, 1.5, c), rng.normal(size=c) * 0.2, rng.normal(size=c) * 0.1, rng.uniform(0.5, 1.5, c)
+    got = pillar_encoder.pillar_feature_net(vox, npv, coors, torch.from_numpy(w).to(cuda), g, b, mu, var, 1e-3,
+                                            cfg["voxel_size"], cfg["point_cloud_range"], num_voxels=nv)
+    want = oracle_mod.pillar_feature_net(vox.cpu().numpy()[:k], npv.cpu().numpy()[:k], coors.cpu().numpy()[:k], w, g, b, mu,
+                                         var, 1e-3, cfg["voxel_size"], cfg["point_cloud_range"])
+    np.testing.assert_allclose(got.cpu().numpy()[:k], want, rtol=1e-4, atol=1e-4 * np.abs(want).max())
+    assert (got.cpu().numpy()[k:] == 0).all()

@@ -176,3 +176,38 @@ def test_cpu_dense_head_vs_torch_fp64(oracle_mod):
             assert g.shape == want.shape
             np.testing.assert_allclose(g, want, rtol=2e-5, atol=2e-5)
     assert got["hm"][1].shape == (1, 2, 20, 28) and got["reg"][0].shape == (1, 2, 20, 28)
+
+
+def test_pillar_feature_net_oracle_vs_torch(oracle_mod):
+    """PFN restatement (PARITY UNPINNED) against the same layer written with torch fp64 ops, incl. the property that
+    zeroed padding rows still take part in the max with the value ReLU(BN(0))."""
+    import torch
+    rng = np.random.default_rng(2)
+    n, m, f, c = 50, 8, 4, 16
+    vs, pcr = [0.16, 0.16, 4.0], [0.0, -39.68, -3.0, 69.12, 39.68, 1.0]
+    npv = rng.integers(1, m + 1, size=n).astype(np.int32)
+    coors = np.stack([np.zeros(n, np.int32), np.zeros(n, np.int32), rng.integers(0, 496, n), rng.integers(0, 432, n)], 1).astype(np.int32)
+    vox = np.zeros((n, m, f), np.float32)
+    for i in range(n):
+        cx, cy = coors[i, 3] * vs[0] + pcr[0], coors[i, 2] * vs[1] + pcr[1]
+        vox[i, :npv[i], 0] = cx + rng.uniform(0, vs[0], npv[i])
+        vox[i, :npv[i], 1] = cy + rng.uniform(0, vs[1], npv[i])
+        vox[i, :npv[i], 2] = rng.uniform(-3, 1, npv[i])
+        vox[i, :npv[i], 3] = rng.uniform(0, 1, npv[i])
+    w = rng.normal(size=(f + 5, c)).astype(np.float32)
+    g, b, mu, var = rng.uniform(0.5, 1.5, c), rng.normal(size=c), rng.normal(size=c) * 0.1, rng.uniform(0.5, 1.5, c)
+    got = oracle_mod.pillar_feature_net(vox, npv, coors, w, g, b, mu, var, 1e-3, vs, pcr)
+    v = torch.from_numpy(vox).double()
+    pm = v[:, :, :3].sum(1, keepdim=True) / torch.from_numpy(npv).double().view(-1, 1, 1)
+    fc = v[:, :, :2].clone()
+    fc[:, :, 0] -= torch.from_numpy(coors[:, 3]).float().view(-1, 1).double() * np.float32(vs[0]) + np.float32(vs[0] / 2 + pcr[0])
+    fc[:, :, 1] -= torch.from_numpy(coors[:, 2]).float().view(-1, 1).double() * np.float32(vs[1]) + np.float32(vs[1] / 2 + pcr[1])
+    feats = torch.cat([v, v[:, :, :3] - pm, fc], -1)
+    mask = (torch.arange(m).view(1, -1) < torch.from_numpy(npv).view(-1, 1)).double().unsqueeze(-1)
+    x = (feats * mask) @ torch.from_numpy(w).double()
+    x = torch.nn.functional.batch_norm(x.transpose(1, 2), torch.from_numpy(mu), torch.from_numpy(var), torch.from_numpy(g),
+                                       torch.from_numpy(b), False, 0.0, 1e-3).transpose(1, 2)
+    want = x.clamp_min(0).max(1).values.numpy()
+    np.testing.assert_allclose(got, want, rtol=1e-5, atol=1e-6)
+    pad = np.maximum((0 - mu) / np.sqrt(var + 1e-3) * g + b, 0)  # what a padding row contributes
+    assert (got[npv < m] >= pad.astype(np.float32) - 1e-6).all()
