@@ -1,0 +1,68 @@
+#!/usr/bin/env python
+"""Per-layer timing of the dense RPN / neck / CenterHead at the C3 shapes (BEV [1, 256, 180, 180]).
+
+Graph-replayed, one JSON line per distinct layer shape with its algorithmic TFLOP/s, then the whole head per-layer
+(`forward`) and batched (`forward_batched`, experimental).  Needs a GPU:  python tools/dense_bench.py [> profiles/...]
+"""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from paddle3d_b200.dense_head import DenseRPNHead, _Conv  # noqa: E402
+from paddle3d_b200.ops import dense_conv as dc  # noqa: E402
+
+
+def graph_time(fn, iters=10):
+    st = torch.cuda.current_stream()
+    fn()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for _ in range(iters):
+            fn()
+    g.replay()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(st)
+    g.replay()
+    b.record(st)
+    b.synchronize()
+    return a.elapsed_time(b) / iters * 1e3  # us
+
+
+def main():
+    dev = torch.device("cuda:0")
+    torch.cuda.set_device(dev)
+    rng = np.random.default_rng(0)
+    H = W = 180
+    shapes = [  # (name, cin, cout, k, stride, pad, up, h, w)
+        ("backbone0 256->128 s1", 256, 128, 3, 1, 1, 1, H, W), ("backbone0 128->128", 128, 128, 3, 1, 1, 1, H, W),
+        ("backbone1 128->256 s2", 128, 256, 3, 2, 1, 1, H, W), ("backbone1 256->256", 256, 256, 3, 1, 1, 1, H // 2, W // 2),
+        ("neck 1x1 128->256", 128, 256, 1, 1, 0, 1, H, W), ("neck deconv 256->256 x2", 256, 256, 2, 2, 0, 2, H // 2, W // 2),
+        ("shared 512->64", 512, 64, 3, 1, 1, 1, H, W), ("head 64->64", 64, 64, 3, 1, 1, 1, H, W),
+        ("heads 64->2304 (36 batched)", 64, 2304, 3, 1, 1, 1, H, W), ("head out 64->3", 64, 3, 3, 1, 1, 1, H, W),
+    ]
+    for name, cin, cout, k, s, p, up, h, w in shapes:
+        conv = _Conv(cin, cout, k, s, p, bias=True, bn_eps=1e-3, up=up).init(rng, dev)
+        x = torch.randn((h * w, 2 * cin), device=dev)
+        want_nchw = cout % 16 != 0
+        us = graph_time(lambda: conv(x, (1, h, w, cin), want_nchw=want_nchw))
+        oh, ow = (h * up, w * up) if up > 1 else ((h + 2 * p - k) // s + 1, (w + 2 * p - k) // s + 1)
+        flops = 2.0 * oh * ow * cin * cout * (1 if up > 1 else k * k)
+        print(json.dumps({"layer": name, "us": round(us, 1), "gflop": round(flops / 1e9, 2),
+                          "algorithmic_tflops": round(flops / us / 1e6, 1)}), flush=True)
+    net = DenseRPNHead(in_channels=256).init_weight(seed=1, device=dev)
+    bev = torch.randn((1, 256, H, W), device=dev)
+    print(json.dumps({"whole_head_per_layer_us": round(graph_time(lambda: net(bev), 3), 1)}), flush=True)
+    if os.environ.get("P3D_EXPERIMENTAL") == "1":
+        print(json.dumps({"whole_head_batched_us": round(graph_time(lambda: net.forward_batched(bev), 3), 1)}), flush=True)
+
+
+if __name__ == "__main__":
+    main()
