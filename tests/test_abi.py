@@ -67,6 +67,36 @@ def test_invalid_arguments_return_status_codes():
     assert L.p3d_nms(None, -1, 0.5, 0, None, None, None, 0, None) == -1
 
 
+def test_invalid_arguments_of_the_conv_entry_points():
+    """Host-side validation of the sparse / dense conv entry points: every call below must be rejected before any
+    CUDA call is made (no GPU here)."""
+    import ctypes as C
+    from paddle3d_b200 import _lib
+    L = _lib.lib()
+    p = C.c_void_p(256)  # a non-null, 16-byte aligned dummy address: the checks below fail before it is touched
+    odd = C.c_void_p(260)  # misaligned
+    # sparse split-row conv: K out of range, missing outputs, misaligned rows, unsupported channel counts
+    assert L.p3d_sparse_conv_gather_gemm_split_ws(p, p, None, 128, 0, 32, 32, p, None, None, None, 0, p, None, None, 0, None) == -1
+    assert L.p3d_sparse_conv_gather_gemm_split_ws(p, p, None, 128, 27, 32, 32, p, None, None, None, 0, None, None, None, 0, None) == -1
+    assert L.p3d_sparse_conv_gather_gemm_split_ws(odd, p, None, 128, 27, 32, 32, p, None, None, None, 0, p, None, None, 0, None) == -1
+    assert L.p3d_sparse_conv_gather_gemm_split_tma(p, 128, p, None, 128, 27, 16, 16, p, None, None, None, 0, p, None, None, 0, None) == -4
+    assert L.p3d_sparse_conv_packed_weight_bytes(27, 5, 16) == 0 and L.p3d_sparse_conv_packed_weight_bytes(27, 16, 16) > 0
+    assert L.p3d_rows_convert_layout(p, 2, None, 16, 16, p, None) == -1
+    # dense conv: channel counts, N tile, transposed-conv geometry, split-row output columns
+    ok = dict(B=1, H=8, W=8)
+    assert L.p3d_dense_conv2d_split(p, 1, 8, 8, 48, p, 64, 64, 3, 3, 1, 1, 1, None, None, 0, p, 64, 0, None, None) == -4
+    assert L.p3d_dense_conv2d_split(p, 1, 8, 8, 64, p, 64, 32, 3, 3, 1, 1, 1, None, None, 0, p, 64, 0, None, None) == -4
+    assert L.p3d_dense_conv2d_split(p, 1, 8, 8, 64, p, 64, 64, 3, 3, 2, 1, 2, None, None, 0, p, 64, 0, None, None) == -4
+    assert L.p3d_dense_conv2d_split(p, 1, 8, 8, 64, p, 64, 64, 3, 3, 1, 1, 1, None, None, 0, None, 64, 0, None, None) == -1
+    assert L.p3d_dense_conv2d_split(p, 1, 8, 8, 64, p, 64, 64, 3, 3, 1, 1, 1, None, None, 0, p, 96, 64, None, None) == -1
+    assert L.p3d_dense_conv2d_packed_weight_bytes(9, 64, 70, 16) == 5 * 9 * 64 * 32 * 4
+    assert L.p3d_dense_conv2d_packed_weight_bytes(9, 48, 64, 64) == 0
+    # grouped head output conv and the pillar encoder
+    assert L.p3d_head_final_conv(p, 1, 8, 8, 128, 64, 3, p, p, p, p, 8, p, None) == -1     # 3 * 64 > 128 channels
+    assert L.p3d_pillar_feature_net(p, p, p, None, 10, 100, 4, 64, p, p, p, p, p, p, None) == -4  # > 64 points / pillar
+    assert L.p3d_pillar_feature_net(p, p, p, None, 10, 32, 4, 64, None, p, p, p, p, p, None) == -1
+
+
 def test_paddle_glue_compiles():
     """paddle_ext/p3d_paddle_ops.cc (the PD_BUILD_OP registrations that bind the C ABI under PaddlePaddle) must at
     least compile against the stub extension header: PaddlePaddle itself is not installable here."""
