@@ -282,3 +282,137 @@ PD_BUILD_OP(bev_pool_v2_bkwd)
     .SetKernelFn(PD_KERNEL(bev_pool_v2_backward))
     .SetInferShapeFn(PD_INFER_SHAPE(BevPoolV2BkwdInferShape))
     .SetInferDtypeFn(PD_INFER_DTYPE(BevPoolV2BkwdInferDtype));
+
+// =====================================================================================================================
+// Ops that have no custom-op counterpart in the reference because their arithmetic lives inside PaddlePaddle
+// (paddle.sparse.nn.SubmConv3D / Conv3D / BatchNorm / ReLU, paddle.scatter, paddle.nn.Conv2D): new op names, same
+// registration style.  paddle3d_b200/ops/sparse_nn.py and dense_head.py are the Python layer mirrors that call the
+// same C entry points through ctypes.
+// =====================================================================================================================
+
+// ---------------------------------------------------------------- p3d_scatter_dense  (pillar_scatter.py:57-105, sparse_resnet.py:202-206)
+std::vector<paddle::Tensor> p3d_scatter_dense_op(const paddle::Tensor &feats, const paddle::Tensor &coords,
+                                                 const paddle::Tensor &num, const int batch, const int D, const int ny,
+                                                 const int nx, const int use_z) {
+  P3D_CHECK_GPU(feats);
+  const int n = static_cast<int>(feats.shape()[0]), C = static_cast<int>(feats.shape()[1]);
+  auto out = paddle::empty({batch, static_cast<int64_t>(C) * D, ny, nx}, paddle::DataType::FLOAT32, paddle::GPUPlace());
+  const size_t ws_bytes = p3d_scatter_dense_workspace_bytes(batch, D, ny, nx);
+  auto ws = workspace(ws_bytes);
+  P3D_CALL(p3d_scatter_dense(feats.data<float>(), coords.data<int>(), num.data<int>(), n, C, batch, D, ny, nx, use_z,
+                             out.data<float>(), ws.data<uint8_t>(), ws_bytes, feats.stream()));
+  return {out};
+}
+std::vector<std::vector<int64_t>> ScatterInferShape(std::vector<int64_t> f, std::vector<int64_t> c, std::vector<int64_t> n,
+                                                    const int &batch, const int &D, const int &ny, const int &nx,
+                                                    const int &use_z) {
+  return {{batch, f[1] * D, ny, nx}};
+}
+std::vector<paddle::DataType> ScatterInferDtype(paddle::DataType f, paddle::DataType c, paddle::DataType n) { return {f}; }
+
+PD_BUILD_OP(p3d_scatter_dense)
+    .Inputs({"FEATS", "COORDS", "NUM"})
+    .Outputs({"OUT"})
+    .Attrs({"batch: int", "D: int", "ny: int", "nx: int", "use_z: int"})
+    .SetKernelFn(PD_KERNEL(p3d_scatter_dense_op))
+    .SetInferShapeFn(PD_INFER_SHAPE(ScatterInferShape))
+    .SetInferDtypeFn(PD_INFER_DTYPE(ScatterInferDtype));
+
+// ---------------------------------------------------------------- rulebooks  (sparse_resnet.py:31-60: SubmConv3D / Conv3D site logic)
+std::vector<paddle::Tensor> p3d_subm_rulebook_op(const paddle::Tensor &coords, const paddle::Tensor &num, const int batch,
+                                                 const std::vector<int> &spatial, const std::vector<int> &ksize) {
+  P3D_CHECK_GPU(coords);
+  const int64_t cap = coords.shape()[0];
+  const int64_t K = static_cast<int64_t>(ksize[0]) * ksize[1] * ksize[2];
+  auto nbr = paddle::empty({cap, K}, paddle::DataType::INT32, paddle::GPUPlace());
+  const size_t ws_bytes = p3d_sparse_rulebook_workspace_bytes(cap, cap);
+  auto ws = workspace(ws_bytes);
+  P3D_CALL(p3d_sparse_rulebook_subm(coords.data<int>(), num.data<int>(), cap, batch, spatial.data(), ksize.data(),
+                                    nbr.data<int>(), ws.data<uint8_t>(), ws_bytes, coords.stream()));
+  return {nbr};
+}
+std::vector<std::vector<int64_t>> SubmRbInferShape(std::vector<int64_t> c, std::vector<int64_t> n, const int &batch,
+                                                   const std::vector<int> &spatial, const std::vector<int> &ksize) {
+  return {{c[0], static_cast<int64_t>(ksize[0]) * ksize[1] * ksize[2]}};
+}
+std::vector<paddle::DataType> SubmRbInferDtype(paddle::DataType c, paddle::DataType n) { return {paddle::DataType::INT32}; }
+
+PD_BUILD_OP(p3d_sparse_subm_rulebook)
+    .Inputs({"COORDS", "NUM"})
+    .Outputs({"NBR"})
+    .Attrs({"batch: int", "spatial: std::vector<int>", "ksize: std::vector<int>"})
+    .SetKernelFn(PD_KERNEL(p3d_subm_rulebook_op))
+    .SetInferShapeFn(PD_INFER_SHAPE(SubmRbInferShape))
+    .SetInferDtypeFn(PD_INFER_DTYPE(SubmRbInferDtype));
+
+std::vector<paddle::Tensor> p3d_conv_rulebook_op(const paddle::Tensor &coords, const paddle::Tensor &num, const int batch,
+                                                 const std::vector<int> &spatial, const std::vector<int> &ksize,
+                                                 const std::vector<int> &stride, const std::vector<int> &padding,
+                                                 const int out_cap) {
+  P3D_CHECK_GPU(coords);
+  const int64_t cap = coords.shape()[0];
+  const int64_t K = static_cast<int64_t>(ksize[0]) * ksize[1] * ksize[2];
+  auto out_coords = paddle::empty({out_cap, 4}, paddle::DataType::INT32, paddle::GPUPlace());
+  auto n_out = paddle::empty({4}, paddle::DataType::INT32, paddle::GPUPlace());  // [count, .., .., table-full flag]
+  auto nbr = paddle::empty({out_cap, K}, paddle::DataType::INT32, paddle::GPUPlace());
+  const size_t ws_bytes = p3d_sparse_rulebook_workspace_bytes(cap, out_cap);
+  auto ws = workspace(ws_bytes);
+  P3D_CALL(p3d_sparse_rulebook_conv(coords.data<int>(), num.data<int>(), cap, batch, spatial.data(), ksize.data(),
+                                    stride.data(), padding.data(), out_coords.data<int>(), n_out.data<int>(), out_cap,
+                                    nbr.data<int>(), ws.data<uint8_t>(), ws_bytes, coords.stream()));
+  return {out_coords, n_out, nbr};
+}
+std::vector<std::vector<int64_t>> ConvRbInferShape(std::vector<int64_t> c, std::vector<int64_t> n, const int &batch,
+                                                   const std::vector<int> &spatial, const std::vector<int> &ksize,
+                                                   const std::vector<int> &stride, const std::vector<int> &padding,
+                                                   const int &out_cap) {
+  return {{out_cap, 4}, {4}, {out_cap, static_cast<int64_t>(ksize[0]) * ksize[1] * ksize[2]}};
+}
+std::vector<paddle::DataType> ConvRbInferDtype(paddle::DataType c, paddle::DataType n) {
+  return {paddle::DataType::INT32, paddle::DataType::INT32, paddle::DataType::INT32};
+}
+
+PD_BUILD_OP(p3d_sparse_conv_rulebook)
+    .Inputs({"COORDS", "NUM"})
+    .Outputs({"OUT_COORDS", "OUT_NUM", "NBR"})
+    .Attrs({"batch: int", "spatial: std::vector<int>", "ksize: std::vector<int>", "stride: std::vector<int>",
+            "padding: std::vector<int>", "out_cap: int"})
+    .SetKernelFn(PD_KERNEL(p3d_conv_rulebook_op))
+    .SetInferShapeFn(PD_INFER_SHAPE(ConvRbInferShape))
+    .SetInferDtypeFn(PD_INFER_DTYPE(ConvRbInferDtype));
+
+// ---------------------------------------------------------------- fused gather-GEMM (+ BN affine + residual + ReLU)
+// RESIDUAL may be a 1-element tensor meaning "none" (Paddle custom ops of this API level have no optional inputs).
+std::vector<paddle::Tensor> p3d_gather_gemm_op(const paddle::Tensor &in, const paddle::Tensor &nbr, const paddle::Tensor &num,
+                                               const paddle::Tensor &weight, const paddle::Tensor &scale,
+                                               const paddle::Tensor &shift, const paddle::Tensor &residual, const int relu,
+                                               const int precision) {
+  P3D_CHECK_GPU(in);
+  const int64_t cap = nbr.shape()[0];
+  const int K = static_cast<int>(nbr.shape()[1]);
+  const int Cin = static_cast<int>(in.shape()[1]);
+  const int Cout = static_cast<int>(weight.shape()[weight.shape().size() - 1]);  // [kD, kH, kW, Cin, Cout]
+  auto out = paddle::empty({cap, Cout}, paddle::DataType::FLOAT32, paddle::GPUPlace());
+  const float *res = residual.numel() > 1 ? residual.data<float>() : nullptr;
+  P3D_CALL(p3d_sparse_conv_gather_gemm(in.data<float>(), nbr.data<int>(), num.data<int>(), cap, K, Cin, Cout,
+                                       weight.data<float>(), scale.data<float>(), shift.data<float>(), res, relu,
+                                       precision, out.data<float>(), in.stream()));
+  return {out};
+}
+std::vector<std::vector<int64_t>> GgInferShape(std::vector<int64_t> in, std::vector<int64_t> nbr, std::vector<int64_t> num,
+                                               std::vector<int64_t> w, std::vector<int64_t> sc, std::vector<int64_t> sh,
+                                               std::vector<int64_t> res, const int &relu, const int &precision) {
+  return {{nbr[0], w[w.size() - 1]}};
+}
+std::vector<paddle::DataType> GgInferDtype(paddle::DataType in, paddle::DataType nbr, paddle::DataType num, paddle::DataType w,
+                                           paddle::DataType sc, paddle::DataType sh, paddle::DataType res) {
+  return {in};
+}
+
+PD_BUILD_OP(p3d_sparse_gather_gemm)
+    .Inputs({"IN", "NBR", "NUM", "WEIGHT", "SCALE", "SHIFT", "RESIDUAL"})
+    .Outputs({"OUT"})
+    .Attrs({"relu: int", "precision: int"})
+    .SetKernelFn(PD_KERNEL(p3d_gather_gemm_op))
+    .SetInferShapeFn(PD_INFER_SHAPE(GgInferShape))
+    .SetInferDtypeFn(PD_INFER_DTYPE(GgInferDtype));

@@ -107,5 +107,7 @@ def test_paddle_glue_compiles():
     assert r.returncode == 0, r.stderr
     src = open(os.path.join(ROOT, "paddle_ext", "p3d_paddle_ops.cc")).read()
     for op in ("hard_voxelize", "boxes_iou_bev_gpu", "boxes_overlap_bev_gpu", "nms_gpu", "nms_normal_gpu",
-               "centerpoint_postprocess", "bev_pool_v2", "bev_pool_v2_bkwd"):
+               "centerpoint_postprocess", "bev_pool_v2", "bev_pool_v2_bkwd",
+               # arithmetic that lives inside PaddlePaddle in the reference: new op names, same registration style
+               "p3d_scatter_dense", "p3d_sparse_subm_rulebook", "p3d_sparse_conv_rulebook", "p3d_sparse_gather_gemm"):
         assert "PD_BUILD_OP(%s)" % op in src
