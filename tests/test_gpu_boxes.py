@@ -154,3 +154,23 @@ def test_bev_pool_v2(cuda, oracle_mod):
     assert np.array_equal(got.cpu().numpy(), oracle_mod.bev_pool_v2(*[d2[k] for k in keys], d2["bev_feat_shape"], use_fma=True))
     e = [targs[0], targs[1]] + [t[:0] for t in targs[2:]]
     assert not bev_pool_v2.bev_pool_v2(*e, d2["bev_feat_shape"]).any()
+
+
+@pytest.mark.skipif(__import__("os").environ.get("P3D_EXPERIMENTAL") != "1", reason="host callers not run on a GPU yet")
+def test_nms_callers_on_device(cuda, oracle_mod):
+    """rotate_nms_pcdet / class_agnostic_nms / boxes_iou3d_gpu with the real GPU ops underneath; the
+    index logic itself is covered on the CPU with the oracle's NMS injected (tests/test_nms_utils.py)."""
+    import torch
+    from paddle3d_b200.ops import nms_utils
+    rng = np.random.default_rng(0)
+    boxes = synth.random_boxes(300, 5)
+    scores = rng.uniform(size=300).astype(np.float32)
+    got = nms_utils.rotate_nms_pcdet(_t(cuda, boxes), _t(cuda, scores), 0.2, 200, 50)
+    b = boxes[:, [0, 1, 2, 4, 3, 5, 6]].copy()
+    b[:, -1] = -b[:, -1] - np.float32(np.pi / 2)
+    order = np.argsort(-scores, kind="stable")[:200]
+    keep, n = oracle_mod.nms(b[order], 0.2)
+    assert np.array_equal(got.cpu().numpy(), order[keep[:n]][:50])
+    a, c = synth.random_boxes(40, 7), synth.random_boxes(30, 8)
+    iou = nms_utils.boxes_iou3d_gpu(_t(cuda, a), _t(cuda, c)).cpu().numpy()
+    assert iou.shape == (40, 30) and (iou >= 0).all() and (iou <= 1 + 1e-5).all()
