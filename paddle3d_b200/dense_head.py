@@ -138,6 +138,34 @@ class DenseRPNHead:
 
     __call__ = forward
 
+    # ---- CenterHead.predict_by_custom_op (center_head.py:294-339): marshal the per-task head tensors
+    def predict_by_custom_op(self, preds, test_cfg, with_velocity=True, example=None, postprocess_fn=None):
+        """preds: forward()'s dict name -> [tensor per task], or the reference's list of per-task dicts.  test_cfg: dict
+        with the yml's keys (voxel_size, point_cloud_range, post_center_limit_range, down_ratio, score_threshold,
+        nms_iou_threshold, nms_pre_max_size, nms_post_max_size).  Returns the reference's one-element list of
+        {meta, box3d_lidar, label_preds, scores}."""
+        if postprocess_fn is None:
+            from .ops.centerpoint_postprocess import centerpoint_postprocess as postprocess_fn
+        if isinstance(preds, dict):
+            preds = [{k: v[t] for k, v in preds.items()} for t in range(len(self.tasks))]
+        hm, reg, height, dim, vel, rot, num_classes, flag = [], [], [], [], [], [], [], 0
+        for task_id, pd in enumerate(preds):
+            for nc in self.tasks:  # as in the reference the list grows to T*T entries; the op reads the first T
+                num_classes.append(flag)
+                flag += nc
+            hm.append(pd["hm"])
+            reg.append(pd["reg"])
+            height.append(pd["height"])
+            dim.append(pd["dim"])
+            vel.append(pd["vel"] if with_velocity else pd["reg"])
+            rot.append(pd["rot"])
+        bboxes, scores, labels = postprocess_fn(
+            hm, reg, height, dim, vel, rot, test_cfg["voxel_size"], test_cfg["point_cloud_range"],
+            test_cfg["post_center_limit_range"], num_classes, test_cfg["down_ratio"], test_cfg["score_threshold"],
+            test_cfg["nms_iou_threshold"], test_cfg["nms_pre_max_size"], test_cfg["nms_post_max_size"], with_velocity)
+        meta = None if not example or not example.get("meta") else example["meta"][0]
+        return [{"meta": meta, "box3d_lidar": bboxes, "label_preds": labels, "scores": scores}]
+
     # ---- EXPERIMENTAL (never run on a GPU yet): the 36 + 36 head convs as two launches
     def _batched_params(self, device):
         """One Conv(64 -> 36 * 64) with the 36 ConvModules' weights / folded BN concatenated along Cout, and the final

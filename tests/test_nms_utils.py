@@ -63,3 +63,26 @@ def test_boxes_iou3d(oracle_mod):
                 - np.maximum(a[:, None, 2] - a[:, None, 5] / 2, b[None, :, 2] - b[None, :, 5] / 2), 0, None)
     va, vb = (a[:, 3] * a[:, 4] * a[:, 5])[:, None], (b[:, 3] * b[:, 4] * b[:, 5])[None, :]
     np.testing.assert_allclose(got, ov * h / np.clip(va + vb - ov * h, 1e-6, None), rtol=1e-5, atol=1e-7)
+
+
+def test_predict_by_custom_op_marshalling():
+    """CenterHead.predict_by_custom_op (center_head.py:294-339): argument order, the num_classes prefix
+    list (first T entries = label offsets), vel falling back to reg, the returned record."""
+    from paddle3d_b200.dense_head import DenseRPNHead
+    net = DenseRPNHead(in_channels=32, out_channels=(32,), layer_nums=(0,), downsample_strides=(1,), fpn_out_channels=(32,),
+                       upsample_strides=(1,), tasks=(1, 2, 2), share_conv_channel=32)
+    preds = {k: [("%s%d" % (k, t)) for t in range(3)] for k in ("hm", "reg", "height", "dim", "vel", "rot")}
+    seen = {}
+
+    def fake(*args):
+        seen["args"] = args
+        return "B", "S", "L"
+
+    cfg = dict(voxel_size=[0.075, 0.075], point_cloud_range=[-54, -54, -5, 54, 54, 3], post_center_limit_range=[-61.2] * 3 + [61.2] * 3,
+               down_ratio=8, score_threshold=0.1, nms_iou_threshold=0.2, nms_pre_max_size=1000, nms_post_max_size=83)
+    out = net.predict_by_custom_op(preds, cfg, with_velocity=False, example={"meta": ["m0"]}, postprocess_fn=fake)
+    a = seen["args"]
+    assert a[0] == ["hm0", "hm1", "hm2"] and a[4] == ["reg0", "reg1", "reg2"] and a[5] == ["rot0", "rot1", "rot2"]
+    assert a[9][:3] == synth.label_offsets((1, 2, 2)) == [0, 1, 3] and len(a[9]) == 9
+    assert a[6] == cfg["voxel_size"] and a[10] == 8 and a[13:16] == (1000, 83, False)
+    assert out == [{"meta": "m0", "box3d_lidar": "B", "label_preds": "L", "scores": "S"}]
