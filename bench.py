@@ -115,7 +115,7 @@ def run_reference(args):
     the reference only implements on the GPU / inside PaddlePaddle.  One step = one full frame."""
     import torch  # noqa: F401  (weights are generated with the same seeded code path as the CUDA arm)
     from paddle3d_b200 import synth
-    from paddle3d_b200.cpu_reference import CpuFrame
+    from oracle.cpu_reference import CpuFrame
     from paddle3d_b200.layers import SparseResNet3D
     from paddle3d_b200.pipeline import CenterPointHotPath
     rank = int(os.environ.get("RANK", "0"))
@@ -386,7 +386,7 @@ def main():
         extra["rooflines_other"] = [hbm_roof]
         # CPU baseline on a bounded sample: one full frame through the oracle port
         if not args.no_cpu_baseline:
-            from paddle3d_b200.cpu_reference import CpuFrame
+            from oracle.cpu_reference import CpuFrame
             import oracle
             cf = CpuFrame(cfg, pipe.export_weights_numpy(), pipe.head_host, pipe.test_cfg, pipe.label_off)
             t2 = time.perf_counter()

@@ -184,6 +184,18 @@ def nms(boxes, thr, normal=False):
     return keep[:n], int(nk)
 
 
+def cpp_nms_mask(bboxes, index, sorted_index, n_for_nms, thr):
+    """Bit-matrix of the postprocess's indexed NMS (centerpoint_postprocess/iou3d_nms_kernel.cu:274-339)."""
+    bboxes = _f(bboxes)
+    index = _i(index)
+    sorted_index = np.ascontiguousarray(sorted_index, dtype=np.int64)
+    cb = (n_for_nms + 63) // 64
+    mask = np.zeros((max(n_for_nms, 1), max(cb, 1)), np.uint64)
+    lib().orc_cpp_nms_mask(_fp(bboxes), _ip(index), sorted_index.ctypes.data_as(C.POINTER(C.c_int64)), int(n_for_nms),
+                           C.c_float(thr), int(bboxes.shape[1]), mask.ctypes.data_as(C.c_void_p))
+    return mask[:n_for_nms, :cb]
+
+
 # --------------------------------------------------------------------------- centerpoint_postprocess
 def centerpoint_postprocess(hm, reg, height, dim, vel, rot, voxel_size, point_cloud_range, post_center_range,
                             num_classes, down_ratio, score_threshold, nms_iou_threshold, nms_pre_max_size,

@@ -159,7 +159,7 @@ class CenterPointHotPath:
         return h2d, d2h
 
     def export_weights_numpy(self):
-        """Weights as plain numpy dicts for the CPU arm (cpu_reference.CpuFrame)."""
+        """Weights as plain numpy dicts for the CPU arm (oracle.cpu_reference.CpuFrame)."""
         def conv(l):
             return dict(weight=l.weight.cpu().numpy(), bias=None if l.bias is None else l.bias.cpu().numpy(),
                         stride=l.stride, padding=l.padding)

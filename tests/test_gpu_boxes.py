@@ -85,6 +85,66 @@ def test_nms_mask_bit_exact_vs_reference_kernel(cuda, oracle_mod):
     assert np.array_equal(m, oracle_mod.nms_mask(boxes, 0.2))  # oracle restatement pinned on the reference kernel
 
 
+def test_nms_normal_mask_vs_reference_kernel(cuda, oracle_mod):
+    """nms_normal (axis-aligned IoU, iou3d_nms_kernel.cu:380-434): the reference kernel's bit-matrix equals the
+    oracle's, and its greedy reduction equals our nms_normal_gpu keep list."""
+    import torch
+    from paddle3d_b200.ops import iou3d_nms
+    ref = oracle_mod.ref_lib("iou3d_gpu")
+    assert ref is not None, "oracle/_ref/libp3d_ref_iou3d_gpu.so must travel to the GPU box"
+    for n, thr in ((1000, 0.3), (257, 0.05)):
+        boxes = synth.random_boxes(n, 500 + n)
+        tb = _t(cuda, boxes)
+        cb = (n + 63) // 64
+        mask = torch.zeros((n, cb), dtype=torch.int64, device=cuda)
+        ref.ref_nms_normal_mask_gpu(C.c_void_p(0), C.c_void_p(tb.data_ptr()), C.c_void_p(mask.data_ptr()), n, C.c_float(thr))
+        torch.cuda.synchronize()
+        m = mask.cpu().numpy().view(np.uint64)
+        assert np.array_equal(m, oracle_mod.nms_mask(boxes, thr, True))
+        keep_ref = np.zeros(n, np.int32)
+        nk = oracle_mod.lib().orc_nms_reduce(m.ctypes.data_as(C.c_void_p), n, keep_ref.ctypes.data_as(C.c_void_p))
+        keep, num = iou3d_nms.nms_normal_gpu(tb, thr)
+        assert int(num[0]) == nk and np.array_equal(keep.numpy()[:nk], keep_ref[:nk])
+
+
+@pytest.mark.parametrize("dims", [9, 7])
+def test_postprocess_indexed_nms_vs_reference_kernel(cuda, oracle_mod, dims):
+    """The indexed NMS of centerpoint_postprocess (centerpoint_postprocess/iou3d_nms_kernel.cu:274-352: boxes fetched
+    through index[sorted_index[i]], w/l swapped, angle -theta - pi/2 evaluated in double): the reference kernel's
+    bit-matrix must equal the oracle's restatement (orc_cpp_nms_mask), which is what our postprocess is checked against,
+    and the greedy reduction of it must equal our p3d_nms on the same re-laid boxes."""
+    import torch
+    from paddle3d_b200.ops import iou3d_nms
+    ref = oracle_mod.ref_lib("cpp_gpu")
+    assert ref is not None, "oracle/_ref/libp3d_ref_cpp_gpu.so must travel to the GPU box"
+    rng = np.random.default_rng(dims)
+    M, n_sel, n_for = 3000, 1500, 1000
+    b7 = synth.random_boxes(M, 11)
+    boxes = np.zeros((M, dims), np.float32)
+    boxes[:, :6] = b7[:, :6]
+    boxes[:, dims - 1] = b7[:, 6]
+    if dims == 9:
+        boxes[:, 6:8] = rng.normal(size=(M, 2)).astype(np.float32)
+    index = rng.choice(M, n_sel, replace=False).astype(np.int32)          # compacted candidate -> cell
+    sorted_index = rng.permutation(n_sel).astype(np.int64)                # score order -> candidate
+    cb = (n_for + 63) // 64
+    mask = torch.zeros((n_for, cb), dtype=torch.int64, device=cuda)
+    tb, ti, ts = _t(cuda, boxes), _t(cuda, index), _t(cuda, sorted_index)
+    ref.ref_cpp_nms_mask_gpu(C.c_void_p(0), C.c_void_p(tb.data_ptr()), C.c_void_p(ti.data_ptr()), C.c_void_p(ts.data_ptr()),
+                             M, n_for, C.c_float(0.2), dims, C.c_void_p(mask.data_ptr()))
+    torch.cuda.synchronize()
+    m = mask.cpu().numpy().view(np.uint64)
+    want = oracle_mod.cpp_nms_mask(boxes, index, sorted_index, n_for, 0.2)
+    assert np.array_equal(m, want), "oracle restatement of the indexed NMS differs from the reference kernel"
+    keep_ref = np.zeros(n_for, np.int32)
+    nk = oracle_mod.lib().orc_nms_reduce(m.ctypes.data_as(C.c_void_p), n_for, keep_ref.ctypes.data_as(C.c_void_p))
+    sel = boxes[index[sorted_index[:n_for]]]
+    relaid = np.stack([sel[:, 0], sel[:, 1], sel[:, 2], sel[:, 4], sel[:, 3], sel[:, 5],
+                       (-sel[:, dims - 1].astype(np.float64) - 3.141592653589793 / 2).astype(np.float32)], 1)
+    keep, num = iou3d_nms.nms_gpu(_t(cuda, relaid), 0.2)
+    assert int(num[0]) == nk and np.array_equal(keep.numpy()[:nk], keep_ref[:nk])
+
+
 def _cpp_args(h, with_velocity=True):
     cfg = synth.CENTERPOINT_TEST_CFG
     return [h["hm"], h["reg"], h["height"], h["dim"], h["vel"], h["rot"], [0.075, 0.075], synth.C3["point_cloud_range"],
@@ -147,6 +207,17 @@ def test_bev_pool_v2(cuda, oracle_mod):
                                                    _t(cuda, rf), _t(cuda, rb), _t(cuda, lens), _t(cuda, starts))
     wdg, wfg = oracle_mod.bev_pool_v2_bkwd(og, d["depth"], d["feat"], rd, rf, rb, lens, starts, use_fma=True)
     assert np.array_equal(dg.cpu().numpy(), wdg) and np.array_equal(fg.cpu().numpy(), wfg)
+    # ... and bit-identical to the reference's own bev_pool_grad_kernel (bev_pool_cuda.cu:46-96) on the entries it
+    # writes (it leaves untouched entries of its caller-zeroed outputs alone; ours writes zeros there)
+    ref = oracle_mod.ref_lib("bevpool_gpu")
+    assert ref is not None, "oracle/_ref/libp3d_ref_bevpool_gpu.so must travel to the GPU box"
+    tg = [_t(cuda, a) for a in (og, d["depth"], d["feat"], rd, rf, rb, starts, lens)]
+    rdg, rfg = torch.zeros_like(tg[1]), torch.zeros_like(tg[2])
+    torch.cuda.synchronize()
+    ref.ref_bev_pool_v2_grad_gpu(d["feat"].shape[-1], len(starts), *[C.c_void_p(t.data_ptr()) for t in tg],
+                                 C.c_void_p(rdg.data_ptr()), C.c_void_p(rfg.data_ptr()))
+    torch.cuda.synchronize()
+    assert torch.equal(rdg, dg) and torch.equal(rfg, fg), "not bit-identical to the reference bev_pool_grad_kernel"
     # odd channel count -> scalar path; empty interval list -> zeros
     d2 = synth.bev_pool_inputs(6, C=7, D=20)
     targs = [_t(cuda, d2[k]) for k in keys]
@@ -156,7 +227,6 @@ def test_bev_pool_v2(cuda, oracle_mod):
     assert not bev_pool_v2.bev_pool_v2(*e, d2["bev_feat_shape"]).any()
 
 
-@pytest.mark.skipif(__import__("os").environ.get("P3D_EXPERIMENTAL") != "1", reason="host callers not run on a GPU yet")
 def test_nms_callers_on_device(cuda, oracle_mod):
     """rotate_nms_pcdet / class_agnostic_nms / boxes_iou3d_gpu with the real GPU ops underneath; the
     index logic itself is covered on the CPU with the oracle's NMS injected (tests/test_nms_utils.py)."""

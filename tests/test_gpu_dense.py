@@ -62,7 +62,7 @@ def test_dense_conv_vs_oracle(cuda, oracle_mod, cin, cout, k, stride, pad, up, h
 
 def test_concat_offset_and_small_head(cuda, oracle_mod):
     import torch
-    from paddle3d_b200.cpu_reference import CpuDenseHead
+    from oracle.cpu_reference import CpuDenseHead
     from paddle3d_b200.dense_head import DenseRPNHead
     net = DenseRPNHead(in_channels=64, out_channels=(32, 64), layer_nums=(1, 2), downsample_strides=(1, 2),
                        fpn_out_channels=(64, 64), upsample_strides=(1, 2), tasks=(1, 2), share_conv_channel=64)
@@ -78,12 +78,11 @@ def test_concat_offset_and_small_head(cuda, oracle_mod):
             assert np.abs(g.cpu().numpy() - w).max() <= 1e-4 * max(1.0, np.abs(w).max()), name
 
 
-@pytest.mark.skipif(__import__("os").environ.get("P3D_EXPERIMENTAL") != "1", reason="never run on a GPU yet")
 def test_batched_head_matches_per_layer_head(cuda, oracle_mod):
     """forward_batched (one 64 -> 36*64 conv + one grouped CUDA-core launch for the output convs) against forward()
     and the CPU reference."""
     import torch
-    from paddle3d_b200.cpu_reference import CpuDenseHead
+    from oracle.cpu_reference import CpuDenseHead
     from paddle3d_b200.dense_head import DenseRPNHead
     net = DenseRPNHead(in_channels=64, out_channels=(32, 64), layer_nums=(1, 1), downsample_strides=(1, 2),
                        fpn_out_channels=(64, 64), upsample_strides=(1, 2), tasks=(1, 2, 2), share_conv_channel=64)

@@ -23,7 +23,7 @@ def _frames(n):
 @pytest.mark.parametrize("precision", [0, 1, 2])
 def test_frame_matches_cpu_oracle_frame(cuda, oracle_mod, precision):
     import torch
-    from paddle3d_b200.cpu_reference import CpuFrame
+    from oracle.cpu_reference import CpuFrame
     pipe = _pipe(cuda, precision)
     pts = _frames(1)[0]
     pipe.points.copy_(torch.from_numpy(pts).to(cuda))
@@ -77,13 +77,12 @@ def test_graph_sweep_and_side_stream_agree_with_eager(cuda):
     assert torch.equal(b, want[1][0]) and torch.equal(side.out["bev"], want[1][3])
 
 
-@pytest.mark.skipif(__import__("os").environ.get("P3D_EXPERIMENTAL") != "1", reason="composition not run on a GPU yet")
 def test_frame_with_dense_head(cuda, oracle_mod):
     """with_head=True: BEV -> DenseRPNHead -> postprocess.  The head tensors must match the CPU reference run on the
     GPU's own BEV tensor (the per-layer and small-network parity is in test_gpu_dense.py); boxes are not compared bit
     for bit because candidates within 1e-4 of the score threshold may flip."""
     import torch
-    from paddle3d_b200.cpu_reference import CpuDenseHead
+    from oracle.cpu_reference import CpuDenseHead
     pipe = _pipe(cuda, 2, with_head=True)
     pipe.points.copy_(torch.from_numpy(_frames(1)[0]).to(cuda))
     with torch.cuda.stream(pipe.stream):

@@ -8,6 +8,7 @@ import numpy as np
 import pytest
 
 from paddle3d_b200 import synth
+from parity import rel_check
 
 pytestmark = pytest.mark.gpu
 
@@ -64,13 +65,13 @@ def test_single_conv(cuda, oracle_mod, precision, subm, ks, st, pd, cin, cout):
                             bn._variance.cpu().numpy(), 1e-3, relu=True)
     assert n == len(oc) and osp == y.index.spatial
     want = _dense(oc, of, B, osp)
-    np.testing.assert_allclose(got, want, rtol=1e-4, atol=1e-4 * np.abs(want).max())
+    rel_check('single_conv p%d %s %d->%d' % (precision, 'subm' if subm else 'conv', cin, cout), got, want)
     if not subm:
         assert int(y.index.counters[1].item()) == 0  # no overflow
     # to_dense_bev == reference to_dense + transpose + reshape
     bev = y.to_dense_bev().cpu().numpy()
     want_bev = np.transpose(want, (0, 4, 1, 2, 3)).reshape(B, cout * osp[0], osp[1], osp[2])
-    np.testing.assert_allclose(bev, want_bev, rtol=1e-4, atol=1e-4 * np.abs(want).max())
+    rel_check('single_conv bev', bev, want_bev)
 
 
 def test_strided_overflow_is_flagged(cuda):
@@ -143,12 +144,11 @@ def test_sparse_resnet3d_small(cuda, oracle_mod, precision):
     got = net(_t(cuda, feats), _t(cuda, coors), 1).cpu().numpy()
     want, pairs = _oracle_resnet(oracle_mod, net, coors, feats, 1)
     assert got.shape == want.shape == (1, 256, 22, 22)
-    scale = np.abs(want).max()
-    np.testing.assert_allclose(got, want, rtol=1e-4, atol=1e-4 * scale)
+    rel_check('sparse_resnet3d_small p%d' % precision, got, want)
     assert (want != 0).mean() > 0.05
 
 
-@pytest.mark.parametrize("precision", [0, 1])
+@pytest.mark.parametrize("precision", PRECISIONS)
 def test_sparsenet3d_small(cuda, oracle_mod, precision):
     """SparseNet3D (sparsenet.py:67-182): dense BEV output and the multi-scale sparse tensors vs the oracle."""
     from paddle3d_b200.layers import SparseNet3D
@@ -173,14 +173,14 @@ def test_sparsenet3d_small(cuda, oracle_mod, precision):
     want = oracle_mod.sparse_to_dense_bev(cc, ff, 1, sp_)
     out = got["spatial_features"].cpu().numpy()
     assert out.shape == want.shape == (1, 256, 22, 22)
-    np.testing.assert_allclose(out, want, rtol=1e-4, atol=1e-4 * np.abs(want).max())
+    rel_check('sparsenet3d_small p%d bev' % precision, out, want)
     for name, (wc, wf, wsp) in zip(["x_conv1", "x_conv2", "x_conv3", "x_conv4"], scales):
         t = got["multi_scale_3d_features"][name]
         m = t.nnz()
         assert m == len(wc) and t.index.spatial == wsp
         gd = _dense(t.index.coords.cpu().numpy()[:m], t.values().cpu().numpy()[:m], 1, wsp)
         wd = _dense(wc, wf, 1, wsp)
-        np.testing.assert_allclose(gd, wd, rtol=1e-4, atol=1e-4 * np.abs(wd).max())
+        rel_check('sparsenet3d_small p%d %s' % (precision, name), gd, wd)
 
 
 def test_hard_voxelizer_batch2(cuda, oracle_mod):

@@ -144,7 +144,6 @@ def test_pillar_scatter(cuda, oracle_mod, cfg, C):
     assert np.array_equal(got2, want2)
 
 
-@pytest.mark.skipif(__import__("os").environ.get("P3D_EXPERIMENTAL") != "1", reason="never run on a GPU yet")
 def test_pillar_feature_net(cuda, oracle_mod):
     """hard_voxelize (C2 geometry) -> PillarFeatureNet against the oracle restatement; 1e-4 relative."""
     import torch

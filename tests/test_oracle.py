@@ -141,7 +141,7 @@ def test_cpu_dense_head_vs_torch_fp64(oracle_mod):
     against the same network written with torch's fp64 CPU ops."""
     import torch
     import torch.nn.functional as F
-    from paddle3d_b200.cpu_reference import CpuDenseHead
+    from oracle.cpu_reference import CpuDenseHead
     from paddle3d_b200.dense_head import DenseRPNHead
     net = DenseRPNHead(in_channels=32, out_channels=(32, 64), layer_nums=(1, 2), downsample_strides=(1, 2),
                        fpn_out_channels=(32, 32), upsample_strides=(1, 2), tasks=(1, 2), share_conv_channel=32)
