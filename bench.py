@@ -204,7 +204,7 @@ def main():
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--precision", default="tf32x3_split", choices=["fp32", "tf32x3", "tf32x3_split", "tf32x3_tma"])
+    ap.add_argument("--precision", default="tf32x3_split", choices=["fp32", "tf32x3", "tf32x3_split", "tf32x3_tma", "f16x3"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--with-head", action="store_true",
                     help="also run the dense RPN/neck/CenterHead (SURVEY 8f-1) and postprocess ITS outputs; not the "
@@ -234,7 +234,8 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     cfg = synth.C3
-    precision = {"tf32x3": sp.TF32X3, "tf32x3_split": sp.TF32X3_SPLIT, "tf32x3_tma": sp.TF32X3_TMA, "fp32": sp.FP32}[args.precision]
+    precision = {"tf32x3": sp.TF32X3, "tf32x3_split": sp.TF32X3_SPLIT, "tf32x3_tma": sp.TF32X3_TMA, "fp32": sp.FP32,
+                 "f16x3": sp.F16X3}[args.precision]
     caps = [int(x) for x in os.environ["P3D_LEVEL_CAPS"].split(",")] if os.environ.get("P3D_LEVEL_CAPS") else None
     pipe = CenterPointHotPath(cfg, dev, precision=precision, seed=0, level_caps=caps, with_head=args.with_head)
     if world > 1:  # weights only: one broadcast over NVLink at start, no per-frame collective
@@ -352,10 +353,10 @@ def main():
             ms = s_ev.elapsed_time(e_ev)
             fl = 2.0 * pairs * cin * cout
             layers.append({"cin": cin, "cout": cout, "rows": rows, "pairs": pairs, "ms": round(ms, 4),
-                           "precision": "tf32x3" if prec in (sp.TF32X3, sp.TF32X3_SPLIT, sp.TF32X3_TMA) else "fp32", "gflop": round(fl / 1e9, 3)})
+                           "precision": "f16x3" if prec == sp.F16X3 else "tf32x3" if prec in (sp.TF32X3, sp.TF32X3_SPLIT, sp.TF32X3_TMA) else "fp32", "gflop": round(fl / 1e9, 3)})
             conv_ms += ms
             conv_flops += fl
-            if prec in (sp.TF32X3, sp.TF32X3_SPLIT, sp.TF32X3_TMA):
+            if prec in (sp.TF32X3, sp.TF32X3_SPLIT, sp.TF32X3_TMA, sp.F16X3):
                 tc_ms += ms
                 tc_flops += fl
         extra["stage_ms_eager"] = stage

@@ -251,6 +251,31 @@ int p3d_sparse_conv_gather_gemm_split_tma(const float *in_split, int64_t n_in_ro
                                           void *workspace, size_t workspace_bytes, p3d_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * fp16-pair ("H16") activations: the default tensor-core path of the sparse layers (csrc/sparse_conv_f16.cu).
+ * x = hi + lo' * 2^-11 with hi = fp16(x), lo' = fp16((x - hi) * 2^11): the same 22 significant bits as the tf32 pair
+ * in half the bytes (a row of C channels is 4*C bytes: groups of KC = min(C, 32) channels, each [hi KC | lo' KC] halfs).
+ * Valid for |x| < 65504; values outside are saturated and bit 0 of *status_dev is set (use the tf32 split path for
+ * such data).  Same layer contract as p3d_sparse_conv_gather_gemm_split (paddle.sparse.nn.SubmConv3D / Conv3D +
+ * BatchNorm(eval) + add + ReLU, sparse_resnet.py:31-60,84-111):
+ *   p3d_sparse_conv_f16_pack_weights   W[K][Cin][Cout] fp32 -> k-blocks of the (hi | lo') weight image
+ *   p3d_rows_convert_h16               to_h16 != 0: fp32 rows [n, C] -> H16 rows; 0: H16 rows -> fp32 rows
+ *   p3d_sparse_conv_f16                persistent kernel, split-K over taps chosen on the device (up to max_splits,
+ *                                      bounded by the workspace); workspace = p3d_sparse_conv_f16_workspace_bytes(...)
+ *                                      bytes whose first align_up(tiles * 4) bytes (tickets) must be ZERO on first use
+ *                                      (the kernel leaves them zero); workspace NULL or max_splits <= 1: no split.
+ * ------------------------------------------------------------------------------------------- */
+size_t p3d_sparse_conv_f16_packed_weight_bytes(int K, int Cin, int Cout);
+int p3d_sparse_conv_f16_pack_weights(const float *weight, int K, int Cin, int Cout, void *packed, int32_t *status_dev,
+                                     p3d_stream_t stream);
+int p3d_rows_convert_h16(const void *src, int to_h16, const int32_t *n_dev, int64_t n_cap, int C, void *dst,
+                         int32_t *status_dev, p3d_stream_t stream);
+size_t p3d_sparse_conv_f16_workspace_bytes(int64_t n_out_cap, int Cout, int max_splits);
+int p3d_sparse_conv_f16(const void *in_h16, const int32_t *nbr, const int32_t *n_out_dev, int64_t n_out_cap, int K,
+                        int Cin, int Cout, const void *packed_weight, const float *scale, const float *shift,
+                        const void *residual_h16, int relu, float *out_f32, void *out_h16, void *workspace,
+                        size_t workspace_bytes, int max_splits, int32_t *status_dev, p3d_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
  * SURVEY.md 8f-1 (parity-green, performance not measured yet): dense 2-D convolution on tcgen05 for the RPN / neck /
  * CenterHead (reference: backbones/second_backbone.py:72-120, necks/second_fpn.py:99-160,
  * detection/centerpoint/center_head.py:43-220).  Images are "pixel split rows" [B*H*W][2][C] (the split-row format

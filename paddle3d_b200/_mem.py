@@ -6,6 +6,7 @@ import torch
 from ._lib import P3DError
 
 _WS = {}
+_RETIRED = []  # outgrown workspaces stay allocated: graphs captured earlier hold their addresses
 
 
 def require_cuda(t, name, dtype=None):
@@ -26,11 +27,16 @@ def stream(device=None):
     return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
-def workspace(nbytes, device, tag="default"):
-    """Grow-only scratch buffer per (device, stream, tag); 256-byte aligned by the caching allocator."""
+def workspace(nbytes, device, tag="default", zero=False):
+    """Grow-only scratch buffer per (device, stream, tag); 256-byte aligned by the caching allocator.  A buffer that
+    is replaced by a larger one is kept alive (a captured CUDA graph may still hold its address).  zero=True:
+    zero-filled when created (for kernels that keep a self-cleaning region in it)."""
     key = (torch.device(device).index, torch.cuda.current_stream(device).cuda_stream, tag)
     buf = _WS.get(key)
     if buf is None or buf.numel() < nbytes:
-        buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+        if buf is not None:
+            _RETIRED.append(buf)
+        alloc = torch.zeros if zero else torch.empty
+        buf = alloc(max(int(nbytes), 256), dtype=torch.uint8, device=device)
         _WS[key] = buf
     return buf

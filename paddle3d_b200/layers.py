@@ -216,7 +216,10 @@ class SparseResNet3D:
             torch.cuda.current_stream(dev).wait_stream(side)
 
     def forward(self, voxel_features, coors, batch_size, num=None):
-        out, _ = self.forward_sparse(voxel_features, coors, batch_size, num)
+        out, feats = self.forward_sparse(voxel_features, coors, batch_size, num)
+        # device counters [n_out, overflow, ...] of the 4 strided index sets: overflow != 0 means output sites were
+        # dropped (capacity from set_level_caps too small) and the BEV tensor is incomplete; callers surface it
+        self.level_counters = [t.index.counters for t in feats[1:]] + [out.index.counters]
         dense = out.to_dense_bev()  # to_dense + transpose(0,4,1,2,3) + reshape [N, C*D, H, W]
         self.join()
         return dense

@@ -29,9 +29,22 @@ from . import pillar_scatter as _ps
 # TF32X3_SPLIT tcgen05 3xTF32 on split-layout rows [n][2][C]: whole-line cp.async gathers, persistent tiles, split done
 #              once in the producing layer's epilogue (fastest measured, what the pipeline and the bench use)
 # TF32X3_TMA   experimental: TF32X3_SPLIT with the row gather of the Cin >= 32 layers done by TMA tile::gather4
-FP32, TF32X3, TF32X3_SPLIT, TF32X3_TMA = 0, 1, 2, 3
-ROWS_F32, ROWS_SPLIT = 0, 1           # activation layouts: [n, C] fp32 | [n][2][C] tf32 hi/lo halves
+# F16X3        tcgen05 on fp16 hi/lo' pair rows (csrc/sparse_conv_f16.cu): same 22-bit products as TF32X3_SPLIT in half
+#              the bytes, persistent + overlapped epilogue + device-chosen split-K; |activations| < 65504 (flagged)
+FP32, TF32X3, TF32X3_SPLIT, TF32X3_TMA, F16X3 = 0, 1, 2, 3, 4
+ROWS_F32, ROWS_SPLIT, ROWS_H16 = 0, 1, 2  # activation layouts: [n, C] fp32 | [n][2][C] tf32 hi/lo | fp16 hi/lo' pairs
 _default_precision = [FP32]
+F16_MAX_SPLITS = 4
+_status = {}
+
+
+def status_tensor(device):
+    """Per-device int32 status word the fp16-pair kernels OR into (bit 0: value outside fp16's range was saturated)."""
+    key = torch.device(device).index
+    t = _status.get(key)
+    if t is None:
+        t = _status[key] = torch.zeros((1,), dtype=torch.int32, device=device)
+    return t
 
 
 def set_precision(p):
@@ -96,7 +109,7 @@ class _Ready:
 class SparseCooTensor:
     def __init__(self, index, values=None, channels=None, pending=None):
         self.index = index
-        self._vals = {ROWS_F32: values, ROWS_SPLIT: None}
+        self._vals = {ROWS_F32: values, ROWS_SPLIT: None, ROWS_H16: None}
         self._pending = pending
         self.channels = channels if channels is not None else values.shape[1]
 
@@ -117,12 +130,29 @@ class SparseCooTensor:
             v = self._vals[layout]
             if v is not None:
                 return v
-        other = 1 - layout
-        src = self._vals[other]
-        dst = torch.empty((self.index.cap, self.channels * (2 if layout == ROWS_SPLIT else 1)), dtype=torch.float32,
-                          device=src.device)
-        check(lib().p3d_rows_convert_layout(ptr(src), other, ptr(self.index.num), self.index.cap, self.channels, ptr(dst),
-                                            stream(src.device)), "rows_convert_layout")
+        f32 = self._vals[ROWS_F32]
+        if f32 is None:  # materialise fp32 rows from whichever pair layout exists
+            if self._vals[ROWS_H16] is not None:
+                src = self._vals[ROWS_H16]
+                f32 = torch.empty((self.index.cap, self.channels), dtype=torch.float32, device=src.device)
+                check(lib().p3d_rows_convert_h16(ptr(src), 0, ptr(self.index.num), self.index.cap, self.channels, ptr(f32),
+                                                 None, stream(src.device)), "rows_convert_h16")
+            else:
+                src = self._vals[ROWS_SPLIT]
+                f32 = torch.empty((self.index.cap, self.channels), dtype=torch.float32, device=src.device)
+                check(lib().p3d_rows_convert_layout(ptr(src), 1, ptr(self.index.num), self.index.cap, self.channels,
+                                                    ptr(f32), stream(src.device)), "rows_convert_layout")
+            self._vals[ROWS_F32] = f32
+        if layout == ROWS_F32:
+            return f32
+        if layout == ROWS_H16:
+            dst = torch.empty((self.index.cap, 2 * self.channels), dtype=torch.float16, device=f32.device)
+            check(lib().p3d_rows_convert_h16(ptr(f32), 1, ptr(self.index.num), self.index.cap, self.channels, ptr(dst),
+                                             ptr(status_tensor(f32.device)), stream(f32.device)), "rows_convert_h16")
+        else:
+            dst = torch.empty((self.index.cap, 2 * self.channels), dtype=torch.float32, device=f32.device)
+            check(lib().p3d_rows_convert_layout(ptr(f32), 0, ptr(self.index.num), self.index.cap, self.channels, ptr(dst),
+                                                stream(f32.device)), "rows_convert_layout")
         self._vals[layout] = dst
         return dst
 
@@ -204,7 +234,21 @@ def _run(p, t, want):
         p.ready.wait(st)
     if PROFILE is not None:
         s_ev, e_ev = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    if p.precision in (TF32X3_SPLIT, TF32X3_TMA):
+    if p.precision == F16X3:
+        xin = p.x.get(ROWS_H16)
+        res = p.residual.get(ROWS_H16) if p.residual is not None else None
+        out_f32 = torch.empty((p.cap, p.cout), dtype=torch.float32, device=dev) if want != ROWS_H16 else None
+        out_h16 = torch.empty((p.cap, 2 * p.cout), dtype=torch.float16, device=dev) if want == ROWS_H16 else None
+        if PROFILE is not None:
+            s_ev.record(st)
+        wsb = L.p3d_sparse_conv_f16_workspace_bytes(p.cap, p.cout, F16_MAX_SPLITS)
+        # one scratch buffer per (capacity, channels): its head holds the self-cleaning split-K tickets (zero on creation)
+        ws = workspace(wsb, dev, "f16_splitk_%d_%d" % (p.cap, p.cout), zero=True) if wsb else None
+        check(L.p3d_sparse_conv_f16(ptr(xin), ptr(p.nbr), ptr(p.num), p.cap, p.K, p.cin, p.cout, ptr(p.weight),
+                                    ptr(p.scale), ptr(p.shift), ptr(res), int(p.relu), ptr(out_f32), ptr(out_h16),
+                                    ptr(ws), wsb, F16_MAX_SPLITS, ptr(status_tensor(dev)), stream(dev)), "sparse_conv_f16")
+        t._vals[ROWS_F32], t._vals[ROWS_H16] = out_f32, out_h16
+    elif p.precision in (TF32X3_SPLIT, TF32X3_TMA):
         xin = p.x.get(ROWS_SPLIT)
         res = p.residual.get(ROWS_SPLIT) if p.residual is not None else None
         out_f32 = torch.empty((p.cap, p.cout), dtype=torch.float32, device=dev) if want == ROWS_F32 else None
@@ -309,16 +353,25 @@ class _ConvBase(_Layer):
             self.bias = torch.from_numpy(b).to(device)
         return self
 
-    def _packed_weight(self, K):
-        """tf32 hi/lo shared-memory image of the weights, built once per layer (p3d_sparse_conv_pack_weights)."""
-        pk = getattr(self, "_packed", None)
+    def _packed_weight(self, K, f16=False):
+        """tf32 hi/lo (or fp16 hi/lo') shared-memory image of the weights, built once per layer."""
+        attr = "_packed_f16" if f16 else "_packed"
+        pk = getattr(self, attr, None)
         if pk is None or pk[0] != self.weight.data_ptr():
             L = lib()
-            nbytes = L.p3d_sparse_conv_packed_weight_bytes(K, self.in_channels, self.out_channels)
-            buf = torch.empty((nbytes // 4,), dtype=torch.float32, device=self.weight.device)
-            check(L.p3d_sparse_conv_pack_weights(ptr(self.weight), K, self.in_channels, self.out_channels, ptr(buf),
-                                                 stream(self.weight.device)), "sparse_conv_pack_weights")
-            self._packed = pk = (self.weight.data_ptr(), buf)
+            dev = self.weight.device
+            if f16:
+                nbytes = L.p3d_sparse_conv_f16_packed_weight_bytes(K, self.in_channels, self.out_channels)
+                buf = torch.empty((nbytes // 4,), dtype=torch.float32, device=dev)
+                check(L.p3d_sparse_conv_f16_pack_weights(ptr(self.weight), K, self.in_channels, self.out_channels, ptr(buf),
+                                                         ptr(status_tensor(dev)), stream(dev)), "sparse_conv_f16_pack_weights")
+            else:
+                nbytes = L.p3d_sparse_conv_packed_weight_bytes(K, self.in_channels, self.out_channels)
+                buf = torch.empty((nbytes // 4,), dtype=torch.float32, device=dev)
+                check(L.p3d_sparse_conv_pack_weights(ptr(self.weight), K, self.in_channels, self.out_channels, ptr(buf),
+                                                     stream(dev)), "sparse_conv_pack_weights")
+            pk = (self.weight.data_ptr(), buf)
+            setattr(self, attr, pk)
         return pk[1]
 
     def set_parameters(self, weight, bias=None):
@@ -361,7 +414,12 @@ class _ConvBase(_Layer):
         p.weight, p.scale, p.shift, p.residual, p.relu = self.weight, None, self.bias, None, False
         p.ready = None
         p.precision = self.precision if self.precision is not None else _default_precision[0]
-        if p.precision in (TF32X3, TF32X3_SPLIT, TF32X3_TMA):
+        if p.precision == F16X3:
+            if not lib().p3d_sparse_conv_f16_packed_weight_bytes(K, self.in_channels, self.out_channels):
+                p.precision = FP32  # e.g. the 5-channel input layer stays on the exact fp32 path
+            else:
+                p.weight = self._packed_weight(K, f16=True)
+        elif p.precision in (TF32X3, TF32X3_SPLIT, TF32X3_TMA):
             if not lib().p3d_sparse_conv_packed_weight_bytes(K, self.in_channels, self.out_channels) or K > 32:
                 p.precision = FP32  # e.g. the 5-channel input layer stays on the exact fp32 path
             else:

@@ -52,6 +52,7 @@ class CenterPointHotPath:
         self.h_scores = torch.empty((rows,), dtype=torch.float32).pin_memory()
         self.h_labels = torch.empty((rows,), dtype=torch.int64).pin_memory()
         self.h_counts = torch.empty((len(self.label_off) + 1,), dtype=torch.int32).pin_memory()
+        self.h_status = torch.zeros((5,), dtype=torch.int32).pin_memory()
 
     # ---- one frame, enqueued on the current stream, device in / device out
     def forward_device(self):
@@ -59,13 +60,15 @@ class CenterPointHotPath:
         mean, coors, npv, nv = vox.voxelize_mean(self.points, cfg["voxel_size"], cfg["point_cloud_range"],
                                                  cfg["max_points"], cfg["max_voxels"], 0)
         bev = self.net(mean, coors, 1, num=nv)
+        # frame status word: [fp16-range overflow of the pair-row kernels, overflow flag of each strided level]
+        status = torch.stack([sp.status_tensor(self.device)[0]] + [c[1] for c in self.net.level_counters])
         h = self.dense(bev) if self.dense is not None else self.head
         boxes, scores, labels, counts = cpp.centerpoint_postprocess_device(
             h["hm"], h["reg"], h["height"], h["dim"], h["vel"], h["rot"], cfg["voxel_size"][:2],
             cfg["point_cloud_range"], tc["post_center_limit_range"], self.label_off, tc["down_ratio"],
             tc["score_threshold"], tc["nms_iou_threshold"], tc["nms_pre_max_size"], tc["nms_post_max_size"], True)
         return dict(bev=bev, boxes=boxes, scores=scores, labels=labels, counts=counts, num_voxels=nv, coors=coors,
-                    mean=mean)
+                    mean=mean, status=status)
 
     def capture(self, warmup=2):
         """Warm up (sizes the workspaces) on the side stream, then capture the frame into a CUDA graph."""
@@ -95,12 +98,26 @@ class CenterPointHotPath:
                 self.out = self.forward_device()
             o = self.out
             self.h_counts.copy_(o["counts"], non_blocking=True)
+            self.h_status.copy_(o["status"], non_blocking=True)
             self.h_boxes.copy_(o["boxes"], non_blocking=True)
             self.h_scores.copy_(o["scores"], non_blocking=True)
             self.h_labels.copy_(o["labels"], non_blocking=True)
         self.stream.synchronize()
+        self.check_status(self.h_status)
         k = int(self.h_counts[-1])
         return self.h_boxes[:k], self.h_scores[:k], self.h_labels[:k]
+
+    @staticmethod
+    def check_status(status_host):
+        """Raise when the frame's device status word reports dropped work (never a silent wrong result)."""
+        st = [int(v) for v in status_host]
+        if st[0]:
+            raise RuntimeError("sparse backbone: an activation left fp16's range (|x| >= 65504) on the fp16-pair path; "
+                               "run this model with precision TF32X3_SPLIT")
+        for lvl, v in enumerate(st[1:]):
+            if v:
+                raise RuntimeError("sparse backbone: strided level %d overflowed its row capacity (set_level_caps); "
+                                   "output sites were dropped" % (lvl + 1))
 
     # ---- public end-to-end call for a sweep of frames: same per-frame work, copies overlapped with compute
     def infer_many(self, frames_host):
@@ -117,7 +134,8 @@ class CenterPointHotPath:
             self._slots = [dict(boxes=torch.empty_like(self.h_boxes).pin_memory(),
                                 scores=torch.empty_like(self.h_scores).pin_memory(),
                                 labels=torch.empty_like(self.h_labels).pin_memory(),
-                                counts=torch.empty_like(self.h_counts).pin_memory()) for _ in range(2)]
+                                counts=torch.empty_like(self.h_counts).pin_memory(),
+                                status=torch.zeros_like(self.h_status).pin_memory()) for _ in range(2)]
             self._staged = [torch.cuda.Event() for _ in range(2)]    # H2D into staging[k] done
             self._consumed = [torch.cuda.Event() for _ in range(2)]  # staging[k] copied into the graph's input
             self._done = [torch.cuda.Event() for _ in range(2)]      # results of slot k are on the host
@@ -126,6 +144,7 @@ class CenterPointHotPath:
         def result(k):
             self._done[k].synchronize()
             sl = self._slots[k]
+            self.check_status(sl["status"])
             n = int(sl["counts"][-1])
             return sl["boxes"][:n].clone(), sl["scores"][:n].clone(), sl["labels"][:n].clone()
 
@@ -144,6 +163,7 @@ class CenterPointHotPath:
                 self.graph.replay()
                 o, sl = self.out, self._slots[k]
                 sl["counts"].copy_(o["counts"], non_blocking=True)
+                sl["status"].copy_(o["status"], non_blocking=True)
                 sl["boxes"].copy_(o["boxes"], non_blocking=True)
                 sl["scores"].copy_(o["scores"], non_blocking=True)
                 sl["labels"].copy_(o["labels"], non_blocking=True)
@@ -155,7 +175,8 @@ class CenterPointHotPath:
 
     def bytes_per_frame(self):
         h2d = self.n * self.F * 4
-        d2h = self.h_boxes.numel() * 4 + self.h_scores.numel() * 4 + self.h_labels.numel() * 8 + self.h_counts.numel() * 4
+        d2h = (self.h_boxes.numel() * 4 + self.h_scores.numel() * 4 + self.h_labels.numel() * 8 + self.h_counts.numel() * 4 +
+               self.h_status.numel() * 4)
         return h2d, d2h
 
     def export_weights_numpy(self):
