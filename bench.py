@@ -1,20 +1,23 @@
 #!/usr/bin/env python
-"""bench.py — CenterPoint hot-path frames/s on B200 (driver contract, see the task's Measurement rules).
+"""bench.py — CenterPoint frames/s on B200 (driver contract, see the task's Measurement rules).
 
   python bench.py [--gpus N] [--steps K] [--warmup W]            this repo's CUDA path
   python bench.py --impl reference [--steps K] [--warmup W]      the reference's CPU arm on the host cores
 
-A step = one pass of the hot path over one synthetic nuScenes-shaped frame (config C3: 300k x 5 points,
-0.075 m voxels, 1440 x 1440 x 40 grid, max 160000 voxels):
-    voxelize+VoxelMean -> SparseResNet3D (21 sparse convs) -> dense BEV -> centerpoint_postprocess.
-The dense 2-D RPN/head between the BEV tensor and the postprocess is not built
-yet, so the postprocess consumes resident synthetic head tensors; `config.workload` says so.
+A step = one synthetic nuScenes-shaped frame (300k x 5 points, 1440 x 1440 x 40 grid, max 160000 voxels) through the
+whole CenterPoint-voxel model:
+    hard_voxelize+VoxelMean -> SparseResNet3D (21 sparse convs) -> dense BEV -> SecondBackbone + SecondFPN + CenterHead
+    (dense RPN / neck / heads, 234 GFLOP) -> centerpoint_postprocess -> boxes.
+Headline geometry: 0.075 m voxels / +-54 m (the heavier one); the 0.1 m / +-72 m geometry BASELINE.json names is
+measured in the same run and reported under `geometry_01m` (--geometry 01 swaps them).  --no-head reproduces the
+round-1 workload (resident synthetic head tensors).
 
 `value`  : frames/s with the frame's points already resident in HBM (CUDA-graph replay per frame).
 `e2e`    : frames/s through the public API CenterPointHotPath.infer_many(): pinned-host points -> H2D ->
-           graph -> D2H of boxes/scores/labels/counts, every step; the H2D of frame i+1 overlaps the compute of
+           graph -> D2H of boxes/scores/labels/counts/status, every step; the H2D of frame i+1 overlaps the compute of
            frame i (copy stream + two staging buffers). `e2e.sync_value` is the one-frame-at-a-time infer() rate.
-`roofline`: dominant kernel, timed live with CUDA events on the launching stream.
+`roofline`: the kernel family with the largest share of the frame (dense conv or sparse conv), `rooflines_other` the
+           rest; timed live with CUDA events on the launching stream.
 N > 1: frame-parallel replicas, one process per GPU (torchrun), weights broadcast once over NCCL,
 no per-frame collective; value = total frames / max-over-ranks time ("weak" scaling).
 """
@@ -31,12 +34,20 @@ sys.path.insert(0, ROOT)
 
 import numpy as np  # noqa: E402
 
-METRIC = "CenterPoint frames/sec @300k pts, 0.075m voxel, 1440x1440x40 grid"
+METRIC = "CenterPoint frames/sec @300k pts, 0.075m voxel (0.1m voxel: geometry_01m), 1440x1440x40 grid"
 UNIT = "frames/s"
-WORKLOAD = ("C3 centerpoint_voxel_0075 hot path: hard_voxelize+VoxelMean -> SparseResNet3D(21 sparse convs) -> "
-            "dense BEV [1,256,180,180] -> centerpoint_postprocess(6 tasks, synthetic head tensors); "
-            "dense 2-D RPN/head (SURVEY §8f-1) not included")
+WORKLOAD = ("CenterPoint-voxel nuScenes-shape frame, 300k x 5 points, 1440x1440x40 grid, %s geometry: hard_voxelize+VoxelMean "
+            "-> SparseResNet3D (21 sparse convs) -> dense BEV [1,256,180,180] -> %s -> centerpoint_postprocess (6 tasks)")
+HEAD_ON = "SecondBackbone + SecondFPN + CenterHead (2 x 6 + 2 + 1 + 36 + 36 convs, 234 GFLOP)"
+HEAD_OFF = "resident synthetic head tensors (dense RPN/head skipped: --no-head)"
 POOL = 32  # distinct frames cycled through: 32 x 6 MB = 192 MB of inputs > 126 MB L2
+
+
+def make_config(geometry, with_head):
+    """The `config` object both arms print (identical dicts: the driver compares them)."""
+    geo = "0.075 m voxels / +-54 m range" if geometry == "0075" else "0.1 m voxels / +-72 m range"
+    return {"workload": WORKLOAD % (geo, HEAD_ON if with_head else HEAD_OFF), "geometry": geometry, "with_head": bool(with_head),
+            "frames_in_pool": POOL, "l2": "input pool 192 MB > 126 MB L2; no explicit flush"}
 
 
 def frame_pool(cfg, n_frames, seed0=0, base=4):
@@ -110,35 +121,57 @@ def peaks():
     return 6650.0, "fallback 6.65 TB/s (B200_PROFILING.md)"
 
 
-def run_reference(args):
-    """CPU arm: the reference's own CPU voxelizer (oracle/_ref, when built) + the oracle port for the stages
-    the reference only implements on the GPU / inside PaddlePaddle.  One step = one full frame."""
-    import torch  # noqa: F401  (weights are generated with the same seeded code path as the CUDA arm)
+def cpu_threads_for_reference():
+    """The CPU arm uses every host core.  torchrun exports OMP_NUM_THREADS=1 to its workers; only rank 0 runs this arm
+    (the other ranks exit), so it takes the whole machine back before the OpenMP runtime of the oracle is loaded."""
+    n = os.cpu_count() or 1
+    os.environ["OMP_NUM_THREADS"] = str(n)
+    return n
+
+
+def build_cpu_frame(cfg, with_head, weights=None, dense_weights=None, head=None):
+    """CpuFrame with the same seeded weights as the CUDA arm (generated on the CPU, no GPU needed)."""
     from paddle3d_b200 import synth
     from oracle.cpu_reference import CpuFrame
     from paddle3d_b200.layers import SparseResNet3D
     from paddle3d_b200.pipeline import CenterPointHotPath
+    if weights is None:
+        class _W:
+            pass
+        w = _W()
+        w.net = SparseResNet3D(cfg["point_dim"], cfg["voxel_size"], cfg["point_cloud_range"]).init_weight(seed=0, device="cpu")
+        weights = CenterPointHotPath.export_weights_numpy(w)
+    if with_head and dense_weights is None:
+        from paddle3d_b200.dense_head import DenseRPNHead
+        dense_weights = DenseRPNHead(in_channels=256).init_weight(seed=1, device=None).export_numpy()
+    if head is None:
+        head = synth.centerpoint_head_outputs(0)
+    return CpuFrame(cfg, weights, head, synth.CENTERPOINT_TEST_CFG, synth.label_offsets(),
+                    dense_weights=dense_weights if with_head else None)
+
+
+def run_reference(args):
+    """CPU arm: the reference's own CPU voxelizer (oracle/_ref, when built) + the oracle port for the stages
+    the reference only implements on the GPU / inside PaddlePaddle.  One step = one full frame."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    cores_set = cpu_threads_for_reference()
+    import torch  # noqa: F401  (weights are generated with the same seeded code path as the CUDA arm)
+    from paddle3d_b200 import synth
     import oracle
-    cfg = synth.C3
-
-    class _W:
-        pass
-    w = _W()
-    w.net = SparseResNet3D(cfg["point_dim"], cfg["voxel_size"], cfg["point_cloud_range"]).init_weight(seed=0, device="cpu")
-    weights = CenterPointHotPath.export_weights_numpy(w)
-    head = synth.centerpoint_head_outputs(0)
-    cf = CpuFrame(cfg, weights, head, synth.CENTERPOINT_TEST_CFG, synth.label_offsets())
-    frames = frame_pool(cfg, 4, base=2)
+    cfg = synth.C3 if args.geometry == "0075" else synth.C3_01
+    with_head = not args.no_head
+    cf = build_cpu_frame(cfg, with_head)
+    frames = frame_pool(cfg, 2, base=2)
     t_w = time.perf_counter()
-    for i in range(args.warmup):
+    n_warm = min(args.warmup, 1)  # a frame costs ~10 s on the host: one untimed frame warms caches / page tables
+    for i in range(n_warm):
         cf.run(frames[i % len(frames)])
-    per_frame = (time.perf_counter() - t_w) / max(args.warmup, 1)
-    # bound the run: a full frame costs seconds on the host, so the number of timed frames is capped at what fits
-    # in about three minutes (the per-frame throughput is what is reported, not a total)
-    steps = max(1, min(args.steps, int(180.0 / max(per_frame, 1e-3))))
+    per_frame = (time.perf_counter() - t_w) / max(n_warm, 1)
+    # bound the run: the number of timed frames is capped at what fits in about two minutes (the per-frame throughput
+    # is what is reported, not a total)
+    steps = max(1, min(args.steps, int(120.0 / max(per_frame, 1e-3))))
     t0 = time.perf_counter()
     stages = {}
     for i in range(steps):
@@ -149,40 +182,46 @@ def run_reference(args):
     requested, args.steps = args.steps, steps
     fps = args.steps / dt
     cores = oracle.num_threads()
-    kind = "port"
-    sample = ("%d full C3 frames; voxelize = %s, voxel_mean/sparse conv/to_dense/postprocess = oracle port "
-              "(OpenMP, %d threads; the reference has no CPU implementation of them)" %
-              (args.steps, "reference hard_voxelize_cpu compiled unmodified (oracle/_ref)" if cf.use_ref else "oracle port", cores))
+    sample = ("%d full frames; voxelize = %s, voxel_mean / sparse conv / to_dense / dense RPN+head / postprocess = oracle "
+              "port (OpenMP, %d threads of %d host cores; the reference has no CPU implementation of them)" %
+              (args.steps, "reference hard_voxelize_cpu compiled unmodified (oracle/_ref)" if cf.use_ref else "oracle port",
+               cores, cores_set))
     line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": {"workload": WORKLOAD},
-            "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+            "warmup": n_warm, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32 (f64 accumulation)", "data": "synthetic",
+            "config": make_config(args.geometry, with_head),
+            "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "stage_ms": {k: 1e3 * v / args.steps for k, v in stages.items()}, "gpu_launches": 0,
             "steps_requested": requested}
     print(json.dumps(line))
 
 
-def kernel_time_ms(fn, stream, iters):
-    """CUDA-event time of `fn` on `stream`, averaged over iters (after one warm call)."""
+def graph_time_ms(fn, stream, iters=5):
+    """Device time of fn(): captured `iters` times into one CUDA graph, replayed, CUDA events on `stream`."""
     import torch
     with torch.cuda.stream(stream):
         fn()
+        stream.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=stream):
+            for _ in range(iters):
+                fn()
+        g.replay()
+        stream.synchronize()
         s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s.record(stream)
-        for _ in range(iters):
-            fn()
+        g.replay()
         e.record(stream)
     e.synchronize()
     return s.elapsed_time(e) / iters
 
 
-def ncu_dram_bytes_per_frame():
-    """dram__bytes_read.sum + dram__bytes_write.sum of the tensor-core sparse-conv launches of ONE frame, from the
-    committed `ncu --set full` capture of this command (profiles/r01_split_ncu_metrics.csv, 20 launches); None when
-    the capture is not in the tree."""
+def ncu_dram_bytes(path_name):
+    """dram__bytes_read.sum + dram__bytes_write.sum summed over the launches of a committed ncu capture
+    (profiles/<path_name>: rows = launches of one frame); None when the capture is not in the tree."""
     import csv
-    path = os.path.join(ROOT, "profiles", "r01_split_ncu_metrics.csv")
+    path = os.path.join(ROOT, "profiles", path_name)
     if not os.path.exists(path):
         return None
     try:
@@ -198,17 +237,123 @@ def ncu_dram_bytes_per_frame():
         return None  # a malformed capture must not take the benchmark down
 
 
+def count_graph_nodes(dot_path):
+    """Nodes of the captured frame graph (kernels, plus the few memset / memcpy nodes torch adds) from its DOT dump."""
+    import re
+    try:
+        txt = open(dot_path).read()
+    except OSError:
+        return None
+    nodes = set(re.findall(r'"?(graph_\w+?_node_\d+)"?\s*\[', txt))
+    return len(nodes) or None
+
+
+def dense_flops(net, H, W):
+    """Algorithmic flops (2 x MACs) of the dense RPN / neck / CenterHead at a BEV of H x W."""
+    total, h, w = 0.0, H, W
+    for blk in net.blocks:
+        for c in blk:
+            h, w = (h + 2 * c.padding - c.k) // c.stride + 1, (w + 2 * c.padding - c.k) // c.stride + 1
+            total += 2.0 * h * w * c.cin * c.cout * c.k * c.k
+    hh, ww = H, W
+    sizes = []
+    h, w = H, W
+    for blk in net.blocks:
+        for c in blk:
+            h, w = (h + 2 * c.padding - c.k) // c.stride + 1, (w + 2 * c.padding - c.k) // c.stride + 1
+        sizes.append((h, w))
+    for (h, w), de in zip(sizes, net.deblocks):
+        total += 2.0 * (h * de.up) * (w * de.up) * de.cin * de.cout * (1 if de.up > 1 else de.k * de.k)
+        hh, ww = h * de.up, w * de.up
+    total += 2.0 * hh * ww * net.shared.cin * net.shared.cout * 9
+    for hs in net.heads:
+        for _, a, f in hs:
+            total += 2.0 * hh * ww * (a.cin * a.cout + f.cin * f.cout) * 9
+    return total
+
+
+def measure(pipe, dev_frames, host_frames, args, world, dist, sample_clocks, local):
+    """Device-timed resident-input rate, e2e (pipelined and one-frame-at-a-time) for one pipeline.  Returns a dict."""
+    import torch
+    st = pipe.stream
+
+    def step_resident(i):
+        with torch.cuda.stream(st):
+            pipe.points.copy_(dev_frames[i % len(dev_frames)], non_blocking=True)  # D2D: the frame is already in HBM
+            pipe.graph.replay()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step_resident(i)
+    barrier()
+    sampler = None
+    if sample_clocks:
+        sampler = ClockSampler(local)
+        sampler.start()
+        time.sleep(0.3)
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t0 = time.perf_counter()
+    s.record(st)
+    for i in range(args.steps):
+        step_resident(i)
+    e.record(st)
+    barrier()
+    wall = time.perf_counter() - t0
+    dev_ms = s.elapsed_time(e)
+    # ---- e2e through the public API (host in, host out), same K
+    for i in range(3):
+        pipe.infer(host_frames[i % len(host_frames)])
+    barrier()
+    t1 = time.perf_counter()
+    n_res = 0
+    for _res in pipe.infer_many(host_frames[i % len(host_frames)] for i in range(args.steps)):  # per-frame H2D + D2H, pipelined
+        n_res += 1
+    assert n_res == args.steps
+    barrier()
+    e2e_s = time.perf_counter() - t1
+    t2 = time.perf_counter()
+    for i in range(args.steps):
+        pipe.infer(host_frames[i % len(host_frames)])   # one frame at a time (latency mode), reported beside the headline
+    barrier()
+    e2e_sync_s = time.perf_counter() - t2
+    clocks = sampler.finish() if sampler is not None else None
+    tt = torch.tensor([dev_ms, e2e_s * 1e3, wall * 1e3, e2e_sync_s * 1e3], dtype=torch.float64, device=pipe.device)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms, wall_ms, sync_ms = [float(x) for x in tt.cpu()]
+    total = args.steps * world
+    return {"value": total / (dev_ms * 1e-3), "ms_per_step": dev_ms / args.steps, "e2e_value": total / (e2e_ms * 1e-3),
+            "e2e_sync_value": total / (sync_ms * 1e-3), "wall_ms_per_step": wall_ms / args.steps, "clocks": clocks}
+
+
+def rel_errors(got, want, floor=1e-2):
+    """Same definition as tests/parity.py: true relative error above floor x max, absolute (over max) below."""
+    got, want = np.asarray(got, np.float64), np.asarray(want, np.float64)
+    scale = float(np.abs(want).max())
+    err = np.abs(got - want)
+    big = np.abs(want) > floor * scale
+    return {"max_rel_above_1e-2_of_max": float((err[big] / np.abs(want[big])).max()) if big.any() else 0.0,
+            "max_abs_below_over_max": float(err[~big].max() / scale) if (~big).any() and scale > 0 else 0.0}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--precision", default="tf32x3_split", choices=["fp32", "tf32x3", "tf32x3_split", "tf32x3_tma", "f16x3"])
+    ap.add_argument("--precision", default="f16x3", choices=["fp32", "tf32x3", "tf32x3_split", "tf32x3_tma", "f16x3"])
+    ap.add_argument("--geometry", default="0075", choices=["0075", "01"], help="headline geometry (the other one is "
+                    "measured as well and reported in `geometry_01m` / `geometry_0075`)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--with-head", action="store_true",
-                    help="also run the dense RPN/neck/CenterHead (SURVEY 8f-1) and postprocess ITS outputs; not the "
-                         "default workload (parity-green, not tuned)")
+    ap.add_argument("--no-head", action="store_true", help="skip the dense RPN / neck / CenterHead (round-1 workload)")
+    ap.add_argument("--no-second-geometry", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
@@ -233,11 +378,12 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
-    cfg = synth.C3
+    with_head = not args.no_head
+    cfg = synth.C3 if args.geometry == "0075" else synth.C3_01
     precision = {"tf32x3": sp.TF32X3, "tf32x3_split": sp.TF32X3_SPLIT, "tf32x3_tma": sp.TF32X3_TMA, "fp32": sp.FP32,
                  "f16x3": sp.F16X3}[args.precision]
     caps = [int(x) for x in os.environ["P3D_LEVEL_CAPS"].split(",")] if os.environ.get("P3D_LEVEL_CAPS") else None
-    pipe = CenterPointHotPath(cfg, dev, precision=precision, seed=0, level_caps=caps, with_head=args.with_head)
+    pipe = CenterPointHotPath(cfg, dev, precision=precision, seed=0, level_caps=caps, with_head=with_head)
     if world > 1:  # weights only: one broadcast over NVLink at start, no per-frame collective
         from paddle3d_b200.sharding import broadcast_weights
         broadcast_weights(pipe.net, 0)
@@ -245,65 +391,38 @@ def main():
     frames = frame_pool(cfg, POOL, seed0=rank * 100)
     dev_frames = [torch.from_numpy(f).to(dev) for f in frames]
     host_frames = [torch.from_numpy(f).pin_memory() for f in frames]
+    pipe.calibrate_head(dev_frames[0])   # random-init heat maps -> ~1.4 % of cells above the score threshold
     pipe.points.copy_(dev_frames[0])
-    pipe.capture()
-    graph_nodes = None
+    dot = os.path.join("/tmp", "p3d_frame_graph_%d.dot" % os.getpid())
+    pipe.capture(dump_path=dot if rank == 0 else None)
+    graph_nodes = count_graph_nodes(dot) if rank == 0 else None
+    if rank == 0 and os.path.isdir(os.path.join(ROOT, "gpurun_out")) and os.path.exists(dot):
+        import shutil
+        shutil.copy(dot, os.path.join(ROOT, "gpurun_out", "frame_graph.dot"))
     st = pipe.stream
+    m = measure(pipe, dev_frames, host_frames, args, world, dist, True, local)
 
-    def step_resident(i):
-        with torch.cuda.stream(st):
-            pipe.points.copy_(dev_frames[i % POOL], non_blocking=True)  # D2D: the frame is already in HBM
-            pipe.graph.replay()
+    # ---- the other geometry, same model, shorter run (reported, not the headline)
+    other = None
+    if not args.no_second_geometry:
+        ogeo = "01" if args.geometry == "0075" else "0075"
+        ocfg = synth.C3_01 if ogeo == "01" else synth.C3
+        opipe = CenterPointHotPath(ocfg, dev, precision=precision, seed=0, level_caps=caps, with_head=with_head)
+        oframes = frame_pool(ocfg, 8, seed0=rank * 100, base=2)
+        odev = [torch.from_numpy(f).to(dev) for f in oframes]
+        ohost = [torch.from_numpy(f).pin_memory() for f in oframes]
+        if opipe.dense is not None:  # same (calibrated) head weights as the headline pipeline
+            for ca, cb in zip(opipe.dense.all_convs(), pipe.dense.all_convs()):
+                ca.np["bias"] = cb.np["bias"]
+            opipe.dense._batched = None
+        opipe.points.copy_(odev[0])
+        opipe.capture()
+        oargs = argparse.Namespace(steps=max(20, args.steps // 4), warmup=max(3, args.warmup // 4))
+        om = measure(opipe, odev, ohost, oargs, world, dist, False, local)
+        other = (ogeo, om, oargs, int(opipe.out["num_voxels"][0].item()))
+        del opipe, odev, ohost
 
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for i in range(args.warmup):
-        step_resident(i)
-    barrier()
-    sampler = ClockSampler(local)
-    sampler.start()
-    time.sleep(0.3)
-    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    t0 = time.perf_counter()
-    s.record(st)
-    for i in range(args.steps):
-        step_resident(i)
-    e.record(st)
-    barrier()
-    wall = time.perf_counter() - t0
-    dev_ms = s.elapsed_time(e)
-    # ---- e2e through the public API (host in, host out), same K
-    for i in range(3):
-        pipe.infer(host_frames[i % POOL])
-    barrier()
-    t1 = time.perf_counter()
-    n_res = 0
-    for _res in pipe.infer_many(host_frames[i % POOL] for i in range(args.steps)):  # per-frame H2D + D2H, pipelined
-        n_res += 1
-    assert n_res == args.steps
-    barrier()
-    e2e_s = time.perf_counter() - t1
-    t2 = time.perf_counter()
-    for i in range(args.steps):
-        pipe.infer(host_frames[i % POOL])   # one frame at a time (latency mode), reported beside the headline
-    barrier()
-    e2e_sync_s = time.perf_counter() - t2
-    clocks = sampler.finish()
-
-    tt = torch.tensor([dev_ms, e2e_s * 1e3, wall * 1e3], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-    dev_ms, e2e_ms, wall_ms = [float(x) for x in tt.cpu()]
-    total_frames = args.steps * world
-    value = total_frames / (dev_ms * 1e-3)
-    e2e_value = total_frames / (e2e_ms * 1e-3)
-
-    # ---- roofline of the dominant kernels, timed live (events on the launching stream), rank 0 only
+    # ---- rooflines of the dominant kernels, timed live (events on the launching stream), rank 0 only
     extra = {}
     if rank == 0:
         hbm_peak, peak_src = peaks()
@@ -311,7 +430,7 @@ def main():
         pts = dev_frames[0]
         # hard_voxelize op (reference API, zero-padded outputs): 4NF + 4VPF + 12V + 4V + 4 bytes
         vox_bytes = 4 * N * F + 4 * V * P * F + 12 * V + 4 * V + 4
-        ms_vox = kernel_time_ms(lambda: vox.hard_voxelize(pts, cfg["voxel_size"], cfg["point_cloud_range"], P, V), st, 20)
+        ms_vox = graph_time_ms(lambda: vox.hard_voxelize(pts, cfg["voxel_size"], cfg["point_cloud_range"], P, V), st, 10)
         # per-stage device times (eager re-run with events; first pass warms the allocator, second is timed)
         from paddle3d_b200.ops import centerpoint_postprocess as cpp
         stage, layers = {}, []
@@ -323,40 +442,42 @@ def main():
                     # park the GPU for ~10 ms so the host enqueues the whole frame first: the events below then
                     # bracket back-to-back kernels, not Python/ctypes launch gaps
                     torch.cuda._sleep(int(2e7))
-                ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)]
+                ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
                 ev[0].record(st)
                 mean, coors, npv, nv = vox.voxelize_mean(pipe.points, cfg["voxel_size"], cfg["point_cloud_range"], P, V, 0)
                 ev[1].record(st)
                 x, _ = pipe.net.forward_sparse(mean, coors, 1, num=nv)
                 x.values()
                 ev[2].record(st)
-                x.to_dense_bev()
+                bev = x.to_dense_bev()
                 pipe.net.join()
                 ev[3].record(st)
-                h, tc = pipe.head, pipe.test_cfg
+                h = pipe.dense(bev) if pipe.dense is not None else pipe.head
+                ev[4].record(st)
+                tc = pipe.test_cfg
                 cpp.centerpoint_postprocess_device(h["hm"], h["reg"], h["height"], h["dim"], h["vel"], h["rot"],
                                                    cfg["voxel_size"][:2], cfg["point_cloud_range"],
                                                    tc["post_center_limit_range"], pipe.label_off, tc["down_ratio"],
                                                    tc["score_threshold"], tc["nms_iou_threshold"],
                                                    tc["nms_pre_max_size"], tc["nms_post_max_size"], True)
-                ev[4].record(st)
-            ev[4].synchronize()
+                ev[5].record(st)
+            ev[5].synchronize()
         prof, sp.PROFILE = sp.PROFILE, None
-        names = ["voxelize_mean", "sparse_backbone(eager: rulebooks + 21 convs)", "to_dense_bev", "postprocess"]
-        for k in range(4):
+        names = ["voxelize_mean", "sparse_backbone(eager: rulebooks + 21 convs)", "to_dense_bev", "dense_rpn_neck_head",
+                 "postprocess"]
+        for k in range(5):
             stage[names[k]] = ev[k].elapsed_time(ev[k + 1])
         nvox = int(nv.item())
-        conv_ms, conv_flops, tc_ms, tc_flops = 0.0, 0.0, 0.0, 0.0
+        tc_ms, tc_flops = 0.0, 0.0
+        tcp = (sp.TF32X3, sp.TF32X3_SPLIT, sp.TF32X3_TMA, sp.F16X3)
         for (cin, cout, K, prec, nbr, num, s_ev, e_ev) in prof:
             rows = int(num[0].item()) if num is not None else nbr.shape[0]
             pairs = int((nbr[:rows] >= 0).sum().item())
             ms = s_ev.elapsed_time(e_ev)
             fl = 2.0 * pairs * cin * cout
             layers.append({"cin": cin, "cout": cout, "rows": rows, "pairs": pairs, "ms": round(ms, 4),
-                           "precision": "f16x3" if prec == sp.F16X3 else "tf32x3" if prec in (sp.TF32X3, sp.TF32X3_SPLIT, sp.TF32X3_TMA) else "fp32", "gflop": round(fl / 1e9, 3)})
-            conv_ms += ms
-            conv_flops += fl
-            if prec in (sp.TF32X3, sp.TF32X3_SPLIT, sp.TF32X3_TMA, sp.F16X3):
+                           "precision": {sp.F16X3: "f16x3", sp.FP32: "fp32"}.get(prec, "tf32x3"), "gflop": round(fl / 1e9, 3)})
+            if prec in tcp:
                 tc_ms += ms
                 tc_flops += fl
         extra["stage_ms_eager"] = stage
@@ -365,79 +486,109 @@ def main():
         pkp = os.path.join(ROOT, "MEASURED_PEAKS.json")
         pk = json.load(open(pkp)) if os.path.exists(pkp) else {}
         bf16_peak = pk.get("bf16_tflops", 1590.0)
-        hbm_roof = {"bound": "hbm", "kernel": "hard_voxelize op (vox_init+insert+rank+slots+write; vox_write dominates)",
-                    "achieved": vox_bytes / (ms_vox * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": vox_bytes / (ms_vox * 1e-3) / 1e9 / hbm_peak, "traffic": None,
-                    "algorithmic_bytes": vox_bytes, "ms": ms_vox, "peak_source": peak_src}
+        tpeak_src = "MEASURED_PEAKS.json bf16_tflops (burst)" if pk else "fallback 1.59 PFLOP/s"
+        rooflines = []
+        rooflines.append({"bound": "hbm", "kernel": "hard_voxelize op (reference API: zero-padded [V, P, F] output)",
+                          "achieved": vox_bytes / (ms_vox * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                          "frac": vox_bytes / (ms_vox * 1e-3) / 1e9 / hbm_peak, "traffic": ncu_dram_bytes("r02_voxelize_ncu_metrics.csv"),
+                          "algorithmic_bytes": vox_bytes, "ms": ms_vox, "peak_source": peak_src})
+        sparse_roof = None
         if tc_ms > 0:
             ach = tc_flops / (tc_ms * 1e-3) / 1e12
-            roof = {"bound": "tensor", "kernel": ("tc2::gather_gemm_split_kernel" if precision in (sp.TF32X3_SPLIT, sp.TF32X3_TMA) else "tc::gather_gemm_tf32x3_kernel") + " (all tensor-core sparse convs of one frame)",
-                    "achieved": ach, "peak": bf16_peak, "unit": "TFLOP/s", "frac": ach / bf16_peak,
-                    "traffic": ncu_dram_bytes_per_frame(),
-                    "algorithmic_flops": tc_flops, "ms": tc_ms,
-                    "peak_source": "MEASURED_PEAKS.json bf16_tflops (burst)" if pk else "fallback 1.59 PFLOP/s",
-                    "note": "achieved counts ALGORITHMIC flops 2*pairs*Cin*Cout; the kernel executes 3 tf32 MMAs per product "
-                            "(3xTF32, tf32 rate = 1/2 bf16) on zero-padded 128-row tiles, so the tensor pipe does "
-                            ">= 6x this work relative to the bf16 peak; the kernels are L2-gather/latency bound"}
-        else:
-            ach = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms else 0.0
-            roof = {"bound": "tensor", "kernel": "gather_gemm_fp32_kernel (CUDA-core fp32 path)", "achieved": ach,
-                    "peak": bf16_peak, "unit": "TFLOP/s", "frac": ach / bf16_peak, "traffic": None, "ms": conv_ms}
-        extra["roofline"] = roof
-        extra["rooflines_other"] = [hbm_roof]
+            kname = {sp.F16X3: "f16::conv_f16_kernel", sp.TF32X3_SPLIT: "tc2::gather_gemm_split_kernel"}.get(precision, "tc::gather_gemm_tf32x3_kernel")
+            sparse_roof = {"bound": "tensor", "kernel": kname + " (the 20 tensor-core sparse convs of one frame)",
+                           "achieved": ach, "peak": bf16_peak, "unit": "TFLOP/s", "frac": ach / bf16_peak,
+                           "traffic": ncu_dram_bytes("r02_f16_ncu_metrics.csv"), "algorithmic_flops": tc_flops, "ms": tc_ms,
+                           "peak_source": tpeak_src,
+                           "note": "achieved counts ALGORITHMIC flops 2*pairs*Cin*Cout; the kernel executes 3 fp16 MMAs per "
+                                   "product on zero-padded 128-row tiles; bound by the row gather (L1TEX wavefronts per gathered "
+                                   "row, profiles/r02_f16_probe.md), not by the tensor pipe"}
+        dense_roof = None
+        if pipe.dense is not None:
+            bev_t = pipe.out["bev"]
+            ms_dense = graph_time_ms(lambda: pipe.dense(bev_t), st, 3)
+            fl = dense_flops(pipe.dense, bev_t.shape[2], bev_t.shape[3])
+            ach = fl / (ms_dense * 1e-3) / 1e12
+            dense_roof = {"bound": "tensor", "kernel": "dcf::dense_conv_f16_kernel (RPN + neck + CenterHead: 16 + 1 + 1 launches)",
+                          "achieved": ach, "peak": bf16_peak, "unit": "TFLOP/s", "frac": ach / bf16_peak,
+                          "traffic": ncu_dram_bytes("r02_dense_ncu_metrics.csv"), "algorithmic_flops": fl, "ms": ms_dense,
+                          "peak_source": tpeak_src,
+                          "note": "achieved counts ALGORITHMIC flops (2 x MACs of the convolutions); the kernel executes 3 fp16 "
+                                  "MMAs per product (fp16-pair operands, 1e-4 parity), i.e. the tensor pipe runs at 3 x "
+                                  "this fraction of the measured fp16/bf16 peak"}
+        cands = [r for r in (dense_roof, sparse_roof) if r is not None]
+        cands.sort(key=lambda r: -r["ms"])
+        if cands:
+            extra["roofline"] = cands[0]
+            rooflines = cands[1:] + rooflines
+        extra["rooflines_other"] = rooflines
         # CPU baseline on a bounded sample: one full frame through the oracle port
         if not args.no_cpu_baseline:
-            from oracle.cpu_reference import CpuFrame
             import oracle
-            cf = CpuFrame(cfg, pipe.export_weights_numpy(), pipe.head_host, pipe.test_cfg, pipe.label_off)
+            dense_w = pipe.dense.export_numpy() if pipe.dense is not None else None
+            cf = build_cpu_frame(cfg, with_head, pipe.export_weights_numpy(), dense_w, pipe.head_host)
             t2 = time.perf_counter()
             r = cf.run(frames[0])
             cpu_s = time.perf_counter() - t2
             extra["cpu_baseline"] = {"value": 1.0 / cpu_s, "unit": UNIT, "cores": oracle.num_threads(), "kind": "port",
-                                     "sample": "1 full C3 frame (frame 0 of the pool); voxelize = %s; other stages = "
+                                     "sample": "1 full frame (frame 0 of the pool); voxelize = %s; other stages = "
                                                "oracle port with OpenMP" % ("reference hard_voxelize_cpu (oracle/_ref)"
                                                                             if cf.use_ref else "oracle port"),
                                      "stage_s": r["times"]}
-            # cross-check while we are here: GPU frame vs CPU frame on the same input
+            # cross-check while we are here: GPU frame vs CPU frame on the same full-size input
             got = pipe.infer(host_frames[0])
-            extra["frame0_check"] = {"labels_equal": bool(np.array_equal(got[2].numpy(), r["labels"])),
-                                     "num_voxels_equal": nvox == r["num_voxels"]}
+            chk = {"num_voxels_equal": nvox == r["num_voxels"], "boxes_gpu": int(len(got[2])), "boxes_cpu": int(len(r["labels"]))}
+            chk["bev"] = rel_errors(pipe.out["bev"].cpu().numpy(), r["bev"])
+            if r["head"] is not None:
+                gh = pipe.dense(pipe.out["bev"])
+                torch.cuda.synchronize()
+                worst = 0.0
+                for name in r["head"]:
+                    for g, wv in zip(gh[name], r["head"][name]):
+                        worst = max(worst, float(np.abs(g.cpu().numpy() - wv).max() / max(1.0, np.abs(wv).max())))
+                chk["head_max_abs_err_over_range"] = worst
+            if len(got[2]) == len(r["labels"]):
+                chk["labels_equal"] = bool(np.array_equal(got[2].numpy(), r["labels"]))
+            extra["frame0_check"] = chk
 
     if rank == 0:
         h2d, d2h = pipe.bytes_per_frame()
-        n_launch = None
-        try:
-            n_launch = len(pipe.graph.debug_dump) if False else None
-        except Exception:
-            pass
-        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f32" if precision == sp.FP32 else "tf32x3(f32 accum)",
-                "data": "synthetic", "config": {"workload": WORKLOAD if not args.with_head else WORKLOAD.replace(
-                    "synthetic head tensors); dense 2-D RPN/head (SURVEY §8f-1) not included",
-                    "head tensors computed by the dense RPN/neck/CenterHead on tcgen05: --with-head, not the default "
-                    "workload); cpu_baseline is for the default workload"), "frames_in_pool": POOL,
-                                                "l2": "input pool 192 MB > 126 MB L2; no explicit flush",
-                                                "parallelism": "frame-parallel x%d (replicas, NCCL weight broadcast only)" % world,
-                                                "precision": args.precision},
-                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+        per_frame_launches = graph_nodes if graph_nodes else pipe_launch_estimate(pipe)
+        line = {"metric": METRIC, "value": m["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": m["ms_per_step"], "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None,
+                "dtype": {"fp32": "f32", "f16x3": "f16x3 (fp16 hi/lo' pairs, f32 accumulation)"}.get(args.precision, "tf32x3 (f32 accumulation)"),
+                "data": "synthetic", "config": make_config(args.geometry, with_head),
+                "parallelism": "frame-parallel x%d (replicas, NCCL weight broadcast only)" % world,
+                "precision": args.precision,
+                "e2e": {"value": m["e2e_value"], "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                         "api": "CenterPointHotPath.infer_many (H2D of frame i+1 overlaps compute of frame i)",
-                        "sync_value": total_frames / e2e_sync_s if world == 1 else None},
-                "gpu_launches": pipe_launch_count(pipe) * args.steps, "clocks": clocks, "wall_ms_per_step": wall_ms / args.steps}
+                        "sync_value": m["e2e_sync_value"] if world == 1 else None},
+                "gpu_launches": per_frame_launches * args.steps,
+                "gpu_launches_per_step": per_frame_launches,
+                "gpu_launches_source": "nodes of the captured CUDA graph (cudaGraphDebugDotPrint)" if graph_nodes else "estimate",
+                "clocks": m["clocks"], "wall_ms_per_step": m["wall_ms_per_step"]}
+        if other is not None:
+            ogeo, om, oargs, onv = other
+            line["geometry_01m" if ogeo == "01" else "geometry_0075"] = {
+                "config": make_config(ogeo, with_head), "value": om["value"], "unit": UNIT, "ms_per_step": om["ms_per_step"],
+                "steps": oargs.steps, "warmup": oargs.warmup, "num_voxels_frame0": onv,
+                "e2e": {"value": om["e2e_value"], "unit": UNIT, "sync_value": om["e2e_sync_value"] if world == 1 else None}}
         line.update(extra)
         print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
 
-def pipe_launch_count(pipe):
-    """Kernels of ours per frame: voxelize front end 5, rulebooks (1 subm x 3 launches... counted explicitly)."""
+def pipe_launch_estimate(pipe):
+    """Fallback when the graph dump is unavailable: kernels of ours per frame, counted from the code."""
     vox_k = 5                      # init, insert, rank, slots, mean
-    rb = 2 + 3 * 2 + 4 * 4 + 0     # res0 subm (insert+nbr) ; res1-3 subm (insert+nbr) ; 4 strided (insert, outputs, finish, nbr)
-    conv = 21
+    rb = 2 + 3 * 2 + 4 * 4         # res0 subm (insert+nbr); res1-3 subm (insert+nbr); 4 strided (insert, outputs, finish, nbr)
+    conv = 21 + 1                  # 21 convs + the fp32 -> fp16-pair conversion after the 5-channel layer
     dense = 2                      # scat_map + scat_write
+    head = (1 + 16 + 1 + 1) if pipe.dense is not None else 0   # layout + 12 backbone + 2 neck + shared + big head conv + finals
     post = 5
-    return vox_k + rb + conv + dense + post
+    return vox_k + rb + conv + dense + head + post
 
 
 if __name__ == "__main__":

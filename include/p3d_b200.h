@@ -302,6 +302,30 @@ int p3d_dense_conv2d_split(const float *in_split, int B, int H, int W, int Cin, 
 int p3d_head_final_conv(const float *in_split, int B, int H, int W, int in_C, int Cin, int groups, const float *weight,
                         const float *bias, const int32_t *plane0_host, const int32_t *cnt_host, int planes,
                         float *out_nchw, p3d_stream_t stream);
+int p3d_head_final_conv_h16(const void *in_h16, int B, int H, int W, int in_C, int Cin, int groups, const float *weight,
+                            const float *bias, const int32_t *plane0_host, const int32_t *cnt_host, int planes,
+                            float *out_nchw, p3d_stream_t stream);
+
+/* fp16-pair dense convolution (csrc/dense_conv_f16.cu): same layer contract as p3d_dense_conv2d_split on pixel H16
+ * rows [B*H*W][C / 32 groups][hi 32 | lo' 32] halfs.  3x3 / stride 1 / pad 1 layers load the haloed tile once per
+ * 32-channel group and read the 9 taps through shifted UMMA descriptors; everything else loads one box per tap.
+ * mode 0 = auto, 1 = force per-tap loads; m_tiles 0 = auto, 1 or 2 M tiles (8 x 16 pixels each) per work item. */
+int p3d_nchw_to_pixel_h16(const float *in, int B, int C, int H, int W, void *out_h16, int32_t *status_dev,
+                          p3d_stream_t stream);
+int p3d_pixel_h16_to_nchw(const void *in_h16, int B, int C, int H, int W, float *out, p3d_stream_t stream);
+size_t p3d_dense_conv2d_f16_packed_weight_bytes(int taps, int Cin, int Cout, int n_tile);
+int p3d_dense_conv2d_f16_pack_weights(const float *weight_tci, int taps, int Cin, int n_tile, void *packed,
+                                      int32_t *status_dev, p3d_stream_t stream);
+/* Grouped 3x3 output convs of the CenterHead (center_head.py:80-117) as one tensor-core launch: group g reads input
+ * channels [g * Cin, (g + 1) * Cin) of the in_C-channel H16 image, uses weight tile g (pack with n_tile = 16, columns
+ * >= cnt[g] zero), bias [groups][16], and writes cnt[g] fp32 planes from plane0[g] (device int32 arrays). */
+int p3d_grouped_head_conv_f16(const void *in_h16, int B, int H, int W, int in_C, int Cin, int groups,
+                              const void *packed_weight, const float *bias, const int32_t *plane0_dev,
+                              const int32_t *cnt_dev, int planes, float *out_nchw, int32_t *status_dev, p3d_stream_t stream);
+int p3d_dense_conv2d_f16(const void *in_h16, int B, int H, int W, int Cin, const void *packed_weight, int Cout, int n_tile,
+                         int kh, int kw, int stride, int pad, int up, const float *scale, const float *shift, int relu,
+                         void *out_h16, int out_C, int out_c0, float *out_nchw, int mode, int m_tiles,
+                         int32_t *status_dev, p3d_stream_t stream);
 
 /* EXPERIMENTAL (never run on a GPU yet), SURVEY.md 8f-2: PillarFeatureNet with one PFNLayer
  * (models/voxel_encoders/pillar_encoder.py:156-210, :81-106) fused into one launch: voxels [n, M, F] + counts + coors

@@ -7,10 +7,13 @@ import numpy as np
 
 
 class CpuFrame:
-    def __init__(self, cfg, weights, head, test_cfg, label_offsets, use_ref_voxelizer=True):
+    def __init__(self, cfg, weights, head, test_cfg, label_offsets, use_ref_voxelizer=True, dense_weights=None):
+        """head: resident head tensors (dict name -> list per task) fed to the postprocess, or - when dense_weights
+        (DenseRPNHead.export_numpy()) is given - ignored: the dense RPN / neck / CenterHead runs on the BEV tensor."""
         import oracle
         self.o = oracle
         self.cfg, self.w, self.head, self.tc, self.off = cfg, weights, head, test_cfg, label_offsets
+        self.dense = CpuDenseHead(dense_weights) if dense_weights is not None else None
         self.use_ref = use_ref_voxelizer and oracle.ref_lib("cpu") is not None
         g = oracle.grid_size(cfg["voxel_size"], cfg["point_cloud_range"])
         self.sparse_shape = [g[2] + 1, g[1], g[0]]
@@ -64,13 +67,19 @@ class CpuFrame:
         bev = o.sparse_to_dense_bev(c, f, 1, sp)
         t["to_dense"] = time.perf_counter() - t0
         t0 = time.perf_counter()
-        h, tc = self.head, self.tc
+        h = self.head
+        if self.dense is not None:
+            h = self.dense.run(bev)
+            t["dense_head"] = time.perf_counter() - t0
+            t0 = time.perf_counter()
+        tc = self.tc
         boxes, scores, labels, _ = o.centerpoint_postprocess(
             h["hm"], h["reg"], h["height"], h["dim"], h["vel"], h["rot"], cfg["voxel_size"][:2], cfg["point_cloud_range"],
             tc["post_center_limit_range"], self.off, tc["down_ratio"], tc["score_threshold"], tc["nms_iou_threshold"],
             tc["nms_pre_max_size"], tc["nms_post_max_size"], True)
         t["postprocess"] = time.perf_counter() - t0
-        return dict(bev=bev, boxes=boxes, scores=scores, labels=labels, times=t, num_voxels=k, pairs=list(self.pairs))
+        return dict(bev=bev, boxes=boxes, scores=scores, labels=labels, times=t, num_voxels=k, pairs=list(self.pairs),
+                    head=h if self.dense is not None else None)
 
 
 class CpuDenseHead:

@@ -68,6 +68,14 @@ SIGNATURES = {
     "p3d_dense_conv2d_packed_weight_bytes": (_sz, [_int, _int, _int, _int]),
     "p3d_pillar_feature_net": (_int, [_vp, _vp, _vp, _vp, _i64, _int, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "p3d_head_final_conv": (_int, [_vp, _int, _int, _int, _int, _int, _int, _vp, _vp, _vp, _vp, _int, _vp, _vp]),
+    "p3d_head_final_conv_h16": (_int, [_vp, _int, _int, _int, _int, _int, _int, _vp, _vp, _vp, _vp, _int, _vp, _vp]),
+    "p3d_nchw_to_pixel_h16": (_int, [_vp, _int, _int, _int, _int, _vp, _vp, _vp]),
+    "p3d_pixel_h16_to_nchw": (_int, [_vp, _int, _int, _int, _int, _vp, _vp]),
+    "p3d_dense_conv2d_f16_packed_weight_bytes": (_sz, [_int, _int, _int, _int]),
+    "p3d_dense_conv2d_f16_pack_weights": (_int, [_vp, _int, _int, _int, _vp, _vp, _vp]),
+    "p3d_grouped_head_conv_f16": (_int, [_vp, _int, _int, _int, _int, _int, _int, _vp, _vp, _vp, _vp, _int, _vp, _vp, _vp]),
+    "p3d_dense_conv2d_f16": (_int, [_vp, _int, _int, _int, _int, _vp, _int, _int, _int, _int, _int, _int, _int, _vp, _vp,
+                                    _int, _vp, _int, _int, _vp, _int, _int, _vp, _vp]),
     "p3d_dense_conv2d_split": (_int, [_vp, _int, _int, _int, _int, _vp, _int, _int, _int, _int, _int, _int, _int, _vp, _vp,
                                       _int, _vp, _int, _int, _vp, _vp]),
     "p3d_sparse_conv_gather_gemm_tf32x3_ws": (_int, [_vp, _vp, _vp, _i64, _int, _int, _int, _vp, _vp, _vp, _vp, _int, _vp,

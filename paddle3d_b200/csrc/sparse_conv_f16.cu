@@ -788,6 +788,18 @@ extern "C" int p3d_sparse_conv_f16_pack_weights(const float *weight, int K, int 
   return P3D_OK;
 }
 
+// dense layers (csrc/dense_conv_f16.cu): the same k-block image for one N tile, W[tap][Cin][n_tile], any Cin % 32 == 0
+extern "C" int p3d_dense_conv2d_f16_pack_weights(const float *weight_tci, int taps, int Cin, int n_tile, void *packed,
+                                                 int32_t *status_dev, p3d_stream_t stream) {
+  if (!weight_tci || !packed || taps < 1 || Cin < 32 || Cin % 32 || (n_tile != 16 && n_tile != 64 && n_tile != 128))
+    return P3D_ERR_INVALID_ARG;
+  const long long total = static_cast<long long>(taps) * Cin * n_tile;
+  f16::pack_weights_kernel<<<div_up(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      weight_tci, taps, Cin, n_tile, static_cast<__half *>(packed), status_dev);
+  P3D_LAUNCH_CHECK();
+  return P3D_OK;
+}
+
 extern "C" int p3d_rows_convert_h16(const void *src, int to_h16, const int32_t *n_dev, int64_t n_cap, int C, void *dst,
                                     int32_t *status_dev, p3d_stream_t stream) {
   if (n_cap < 0 || C < 16 || (C != 16 && C % 32) || (n_cap && (!src || !dst))) return P3D_ERR_INVALID_ARG;

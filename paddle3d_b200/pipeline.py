@@ -1,8 +1,8 @@
 """CenterPoint-voxel hot-path frame on one B200: the public API a user calls (bench.py `e2e`).
 
     voxelize (+ VoxelMean fused)  ->  SparseResNet3D (21 sparse convs)  ->  dense BEV [1,256,180,180]
-    -> [dense 2-D RPN + CenterHead: SURVEY.md §8f rank 1, NOT built yet: head tensors are synthetic] ->
-    centerpoint_postprocess -> boxes
+    -> dense 2-D RPN + neck + CenterHead (with_head=True; otherwise resident synthetic head tensors)
+    -> centerpoint_postprocess -> boxes
 
 Everything between the H2D copy of the points and the D2H copy of the boxes is captured once in a
 CUDA graph (data-dependent row counts live in device scalars, buffers are sized by capacity), so a
@@ -70,15 +70,39 @@ class CenterPointHotPath:
         return dict(bev=bev, boxes=boxes, scores=scores, labels=labels, counts=counts, num_voxels=nv, coors=coors,
                     mean=mean, status=status)
 
-    def capture(self, warmup=2):
-        """Warm up (sizes the workspaces) on the side stream, then capture the frame into a CUDA graph."""
+    def calibrate_head(self, points_dev):
+        """Shift the heat-map biases of the (randomly initialised) dense head so that ~1.4 % of the BEV cells of this frame
+        score above the threshold, as SURVEY.md §8d specifies for the synthetic workload (see
+        DenseRPNHead.calibrate_heatmap_bias).  Call before capture()."""
+        if self.dense is None:
+            return self
+        cfg = self.cfg
+        with torch.cuda.stream(self.stream):
+            self.points.copy_(points_dev)
+            mean, coors, npv, nv = vox.voxelize_mean(self.points, cfg["voxel_size"], cfg["point_cloud_range"],
+                                                     cfg["max_points"], cfg["max_voxels"], 0)
+            bev = self.net(mean, coors, 1, num=nv)
+            self.dense.calibrate_heatmap_bias(bev, self.test_cfg["score_threshold"])
+        self.stream.synchronize()
+        return self
+
+    def capture(self, warmup=2, dump_path=None):
+        """Warm up (sizes the workspaces) on the side stream, then capture the frame into a CUDA graph.  dump_path: also
+        write the graph's DOT description there (cudaGraphDebugDotPrint) so callers can count its nodes."""
         with torch.cuda.stream(self.stream):
             for _ in range(warmup):
                 self.out = self.forward_device()
             self.stream.synchronize()
             self.graph = torch.cuda.CUDAGraph()
+            if dump_path is not None:
+                self.graph.enable_debug_mode()
             with torch.cuda.graph(self.graph, stream=self.stream):
                 self.out = self.forward_device()
+            if dump_path is not None:
+                try:
+                    self.graph.debug_dump(dump_path)
+                except Exception:  # noqa: BLE001  (a debugging aid must not take the pipeline down)
+                    pass
         self.stream.synchronize()
         return self
 

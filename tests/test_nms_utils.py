@@ -70,7 +70,7 @@ def test_predict_by_custom_op_marshalling():
     list (first T entries = label offsets), vel falling back to reg, the returned record."""
     from paddle3d_b200.dense_head import DenseRPNHead
     net = DenseRPNHead(in_channels=32, out_channels=(32,), layer_nums=(0,), downsample_strides=(1,), fpn_out_channels=(32,),
-                       upsample_strides=(1,), tasks=(1, 2, 2), share_conv_channel=32)
+                       upsample_strides=(1,), tasks=(1, 2, 2), share_conv_channel=32, with_velocity=False)
     preds = {k: [("%s%d" % (k, t)) for t in range(3)] for k in ("hm", "reg", "height", "dim", "vel", "rot")}
     seen = {}
 
@@ -78,9 +78,10 @@ def test_predict_by_custom_op_marshalling():
         seen["args"] = args
         return "B", "S", "L"
 
+    # the yml's nested form (test_cfg.nms.*), positional order of the reference call site (centerpoint.py:163)
     cfg = dict(voxel_size=[0.075, 0.075], point_cloud_range=[-54, -54, -5, 54, 54, 3], post_center_limit_range=[-61.2] * 3 + [61.2] * 3,
-               down_ratio=8, score_threshold=0.1, nms_iou_threshold=0.2, nms_pre_max_size=1000, nms_post_max_size=83)
-    out = net.predict_by_custom_op(preds, cfg, with_velocity=False, example={"meta": ["m0"]}, postprocess_fn=fake)
+               down_ratio=8, score_threshold=0.1, nms=dict(nms_iou_threshold=0.2, nms_pre_max_size=1000, nms_post_max_size=83))
+    out = net.predict_by_custom_op({"meta": ["m0"]}, preds, cfg, postprocess_fn=fake)
     a = seen["args"]
     assert a[0] == ["hm0", "hm1", "hm2"] and a[4] == ["reg0", "reg1", "reg2"] and a[5] == ["rot0", "rot1", "rot2"]
     assert a[9][:3] == synth.label_offsets((1, 2, 2)) == [0, 1, 3] and len(a[9]) == 9
