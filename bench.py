@@ -332,6 +332,62 @@ def measure(pipe, dev_frames, host_frames, args, world, dist, sample_clocks, loc
             "e2e_sync_value": total / (sync_ms * 1e-3), "wall_ms_per_step": wall_ms / args.steps, "clocks": clocks}
 
 
+def reference_gpu_race(dev, stream):
+    """The reference's own Paddle-free CUDA kernels (compiled unmodified into oracle/_ref, the "kernels to beat" of
+    SURVEY §8d-ii) timed beside this repo's ops, same process, same inputs, CUDA events.  Baseline leg only."""
+    import ctypes as C
+    import torch
+    import oracle
+    from paddle3d_b200 import synth
+    from paddle3d_b200.ops import bev_pool_v2, iou3d_nms
+    out = {}
+
+    def ev_time(fn, iters=20):
+        torch.cuda.synchronize()
+        fn()
+        torch.cuda.synchronize()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(iters):
+            fn()
+        e.record()
+        e.synchronize()
+        return s.elapsed_time(e) / iters * 1e3  # us
+
+    ref = oracle.ref_lib("iou3d_gpu")
+    if ref is not None:
+        a = torch.from_numpy(synth.random_boxes(1000, 3)).to(dev)
+        b = torch.from_numpy(synth.random_boxes(1000, 4)).to(dev)
+        want = torch.empty((1000, 1000), dtype=torch.float32, device=dev)
+        mask = torch.zeros((1000, 16), dtype=torch.int64, device=dev)
+        out["boxes_iou_bev 1000x1000"] = {
+            "reference_us": ev_time(lambda: ref.ref_boxes_iou_bev_gpu(C.c_void_p(0), 1000, C.c_void_p(a.data_ptr()), 1000,
+                                                                       C.c_void_p(b.data_ptr()), C.c_void_p(want.data_ptr()))),
+            "ours_us": ev_time(lambda: iou3d_nms.boxes_iou_bev_gpu(a, b))}
+        out["nms 1000 boxes"] = {
+            "reference_us": ev_time(lambda: ref.ref_nms_mask_gpu(C.c_void_p(0), C.c_void_p(a.data_ptr()), C.c_void_p(mask.data_ptr()),
+                                                                  1000, C.c_float(0.2))),
+            "ours_us": ev_time(lambda: iou3d_nms.nms_gpu(a, 0.2, device_outputs=True)),
+            "note": "reference = bit-matrix kernel only (its greedy pass runs on the host after a D2H copy, iou3d_nms.cpp:115-135); "
+                    "ours = bit-matrix + greedy on the device"}
+    ref = oracle.ref_lib("bevpool_gpu")
+    if ref is not None:
+        for grid, bd in (((128, 128, 1), (-51.2, 51.2)), ((200, 200, 1), (-50.0, 50.0))):
+            d = synth.bev_pool_inputs(5, grid=grid, bounds=(bd, bd, (-5.0, 3.0)))
+            keys = ["depth", "feat", "ranks_depth", "ranks_feat", "ranks_bev", "interval_lengths", "interval_starts"]
+            t = [torch.from_numpy(d[k]).to(dev) for k in keys]
+            o = torch.zeros(d["bev_feat_shape"], dtype=torch.float32, device=dev)
+            p = [C.c_void_p(x.data_ptr()) for x in t]
+            out["bev_pool_v2 %dx%d" % grid[:2]] = {
+                "reference_us": ev_time(lambda: ref.ref_bev_pool_v2_gpu(d["feat"].shape[-1], len(d["interval_starts"]), p[0], p[1], p[2],
+                                                                         p[3], p[4], p[6], p[5], C.c_void_p(o.data_ptr()))),
+                "ours_us": ev_time(lambda: bev_pool_v2.bev_pool_v2(*t, d["bev_feat_shape"])),
+                "note": "ours includes the zero fill of the output (the reference op does it in a separate paddle.full)"}
+    for v in out.values():
+        v["speedup"] = v["reference_us"] / v["ours_us"]
+    return out
+
+
 def rel_errors(got, want, floor=1e-2):
     """Same definition as tests/parity.py: true relative error above floor x max, absolute (over max) below."""
     got, want = np.asarray(got, np.float64), np.asarray(want, np.float64)
@@ -550,6 +606,10 @@ def main():
             if len(got[2]) == len(r["labels"]):
                 chk["labels_equal"] = bool(np.array_equal(got[2].numpy(), r["labels"]))
             extra["frame0_check"] = chk
+            try:
+                extra["reference_gpu"] = reference_gpu_race(dev, st)
+            except Exception as e:  # noqa: BLE001  (a side measurement must not take the headline down)
+                extra["reference_gpu"] = {"error": repr(e)}
 
     if rank == 0:
         h2d, d2h = pipe.bytes_per_frame()

@@ -316,6 +316,19 @@ int p3d_pixel_h16_to_nchw(const void *in_h16, int B, int C, int H, int W, float 
 size_t p3d_dense_conv2d_f16_packed_weight_bytes(int taps, int Cin, int Cout, int n_tile);
 int p3d_dense_conv2d_f16_pack_weights(const float *weight_tci, int taps, int Cin, int n_tile, void *packed,
                                       int32_t *status_dev, p3d_stream_t stream);
+/* ---------------------------------------------------------------------------------------------
+ * bev_pool rank preparation      replaces LSSViewTransformer.voxel_pooling_prepare_v2
+ *   (paddle3d/models/transformers/bevdet_transformer.py:230-274): frustum points coor [B, N, D, H, W, 3] fp32 ->
+ *   ranks_bev / ranks_depth / ranks_feat sorted by ranks_bev (ties: ascending point index = stable argsort),
+ *   interval_starts / interval_lengths; all outputs int32 [B*N*D*H*W] (capacity), counts_dev = {n_kept, n_intervals}.
+ *   Entries beyond the counts are zero.  grid_size_host = (X, Y, Z) cells, lower bound / interval per axis (x, y, z).
+ * ------------------------------------------------------------------------------------------- */
+size_t p3d_bev_pool_prepare_workspace_bytes(int64_t num_points);
+int p3d_bev_pool_prepare(const float *coor, int B, int N, int D, int H, int W, const float *grid_lower_bound_host,
+                         const float *grid_interval_host, const int32_t *grid_size_host, int32_t *ranks_bev,
+                         int32_t *ranks_depth, int32_t *ranks_feat, int32_t *interval_starts, int32_t *interval_lengths,
+                         int32_t *counts_dev, void *workspace, size_t workspace_bytes, p3d_stream_t stream);
+
 /* Grouped 3x3 output convs of the CenterHead (center_head.py:80-117) as one tensor-core launch: group g reads input
  * channels [g * Cin, (g + 1) * Cin) of the in_C-channel H16 image, uses weight tile g (pack with n_tile = 16, columns
  * >= cnt[g] zero), bias [groups][16], and writes cnt[g] fp32 planes from plane0[g] (device int32 arrays). */

@@ -184,6 +184,42 @@ def nms(boxes, thr, normal=False):
     return keep[:n], int(nk)
 
 
+def voxel_pooling_prepare_v2(coor, grid_lower_bound, grid_interval, grid_size):
+    """numpy restatement of LSSViewTransformer.voxel_pooling_prepare_v2
+    (paddle3d/models/transformers/bevdet_transformer.py:230-274), line by line; the `argsort` (:260) is taken as a
+    STABLE sort (ties keep ascending point index): Paddle's tie order is upstream and unspecified, this is the order the
+    repo defines and the CUDA path reproduces.  Returns (ranks_bev, ranks_depth, ranks_feat, interval_starts,
+    interval_lengths) int32, or five Nones as the reference does."""
+    coor = np.asarray(coor, np.float32)
+    B, N, D, H, W, _ = coor.shape
+    num_points = B * N * D * H * W
+    ranks_depth = np.arange(num_points, dtype=np.int64)                                   # :235
+    ranks_feat = np.arange(num_points // D, dtype=np.int64).reshape(B, N, 1, H, W)         # :236-238
+    ranks_feat = np.broadcast_to(ranks_feat, (B, N, D, H, W)).reshape(-1)
+    lower = np.asarray(grid_lower_bound, np.float32)
+    interval = np.asarray(grid_interval, np.float32)
+    c = ((coor - lower) / interval)                                                        # :240-242 (fp32)
+    with np.errstate(invalid="ignore"):
+        c = np.trunc(c).astype(np.int64).reshape(num_points, 3)                            # :243 cast('int64'): toward zero
+    batch_idx = np.repeat(np.arange(B), num_points // B)                                   # :244-246
+    gx, gy, gz = [int(v) for v in grid_size]
+    kept = (c[:, 0] >= 0) & (c[:, 0] < gx) & (c[:, 1] >= 0) & (c[:, 1] < gy) & (c[:, 2] >= 0) & (c[:, 2] < gz)  # :249-251
+    if kept.sum() == 0:
+        return None, None, None, None, None
+    c, ranks_depth, ranks_feat, batch_idx = c[kept], ranks_depth[kept], ranks_feat[kept], batch_idx[kept]
+    ranks_bev = batch_idx * (gz * gy * gx) + c[:, 2] * (gy * gx) + c[:, 1] * gx + c[:, 0]   # :256-259
+    order = np.argsort(ranks_bev, kind="stable")                                           # :260
+    ranks_bev, ranks_depth, ranks_feat = ranks_bev[order], ranks_depth[order], ranks_feat[order]
+    first = np.ones(len(ranks_bev), bool)                                                  # :264-265
+    first[1:] = ranks_bev[1:] != ranks_bev[:-1]
+    interval_starts = np.nonzero(first)[0].astype(np.int32)                                # :266
+    interval_lengths = np.zeros_like(interval_starts)                                      # :269-271
+    interval_lengths[:-1] = interval_starts[1:] - interval_starts[:-1]
+    interval_lengths[-1] = len(ranks_bev) - interval_starts[-1]
+    return (ranks_bev.astype(np.int32), ranks_depth.astype(np.int32), ranks_feat.astype(np.int32), interval_starts,
+            interval_lengths.astype(np.int32))
+
+
 def cpp_nms_mask(bboxes, index, sorted_index, n_for_nms, thr):
     """Bit-matrix of the postprocess's indexed NMS (centerpoint_postprocess/iou3d_nms_kernel.cu:274-339)."""
     bboxes = _f(bboxes)

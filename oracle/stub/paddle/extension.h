@@ -26,7 +26,7 @@
 
 namespace paddle {
 
-enum class DataType { BOOL, UINT8, INT32, INT64, FLOAT32, FLOAT64 };
+enum class DataType { BOOL, UINT8, INT32, INT64, FLOAT16, FLOAT32, FLOAT64 };
 
 struct CPUPlace {};
 struct GPUPlace {};
@@ -37,6 +37,7 @@ inline size_t p3d_stub_sizeof(DataType t) {
     case DataType::UINT8: return 1;
     case DataType::INT32: return 4;
     case DataType::INT64: return 8;
+    case DataType::FLOAT16: return 2;
     case DataType::FLOAT32: return 4;
     case DataType::FLOAT64: return 8;
   }
@@ -70,6 +71,7 @@ class Tensor {
   bool is_gpu_pinned() const { return false; }
   template <typename T>
   T* data() const { return reinterpret_cast<T*>(buf_.get()); }
+  void* data() const { return buf_.get(); }  // paddle::Tensor's untyped accessor
   // compile-check-only surface used by paddle_ext/ (never executed in this repo)
   void* stream() const { return nullptr; }
   template <typename P>

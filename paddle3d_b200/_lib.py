@@ -73,6 +73,9 @@ SIGNATURES = {
     "p3d_pixel_h16_to_nchw": (_int, [_vp, _int, _int, _int, _int, _vp, _vp]),
     "p3d_dense_conv2d_f16_packed_weight_bytes": (_sz, [_int, _int, _int, _int]),
     "p3d_dense_conv2d_f16_pack_weights": (_int, [_vp, _int, _int, _int, _vp, _vp, _vp]),
+    "p3d_bev_pool_prepare_workspace_bytes": (_sz, [_i64]),
+    "p3d_bev_pool_prepare": (_int, [_vp, _int, _int, _int, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz,
+                                    _vp]),
     "p3d_grouped_head_conv_f16": (_int, [_vp, _int, _int, _int, _int, _int, _int, _vp, _vp, _vp, _vp, _int, _vp, _vp, _vp]),
     "p3d_dense_conv2d_f16": (_int, [_vp, _int, _int, _int, _int, _vp, _int, _int, _int, _int, _int, _int, _int, _vp, _vp,
                                     _int, _vp, _int, _int, _vp, _int, _int, _vp, _vp]),

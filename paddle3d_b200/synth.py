@@ -19,6 +19,9 @@ C3 = dict(name="centerpoint_voxel_0075", num_points=300000, point_dim=5, voxel_s
 C3_01 = dict(name="centerpoint_voxel_01", num_points=300000, point_dim=5, voxel_size=[0.1, 0.1, 0.2],
              point_cloud_range=[-72.0, -72.0, -5.0, 72.0, 72.0, 3.0], max_points=10, max_voxels=160000)
 C1 = dict(C2, name="c1_cpu", num_points=1000)
+# LiDAR branch of BEVFusion (configs/bevfusion/bevf_pp_2x8_1x_nusc.yaml:87-105): 0.25 m pillars on a 400 x 400 grid
+C4_LIDAR = dict(name="bevfusion_lidar_pillars", num_points=300000, point_dim=4, voxel_size=[0.25, 0.25, 8.0],
+                point_cloud_range=[-50.0, -50.0, -5.0, 50.0, 50.0, 3.0], max_points=64, max_voxels=40000)
 
 CENTERPOINT_TASKS = [1, 2, 2, 1, 2, 2]  # classes per task (yml:139-151)
 CENTERPOINT_TEST_CFG = dict(  # yml:163-172
@@ -183,7 +186,8 @@ def bev_pool_inputs(seed, n_cams=6, D=118, H=16, W=44, C=80, grid=(128, 128, 1),
     feat = rng.normal(0, 1, size=(B * N, H, W, C)).astype(np.float32)
     return dict(depth=depth, feat=feat, ranks_depth=ranks_depth.astype(np.int32), ranks_feat=ranks_feat.astype(np.int32),
                 ranks_bev=ranks_bev.astype(np.int32), interval_starts=interval_starts,
-                interval_lengths=interval_lengths.astype(np.int32), bev_feat_shape=(B, gy, gx, C))
+                interval_lengths=interval_lengths.astype(np.int32), bev_feat_shape=(B, gy, gx, C),
+                coor=coor, grid_lower_bound=lower, grid_interval=interval, grid_size=(gx, gy, gz))
 
 
 def kaiming_uniform(rng, shape, fan_in):

@@ -416,3 +416,145 @@ PD_BUILD_OP(p3d_sparse_gather_gemm)
     .SetKernelFn(PD_KERNEL(p3d_gather_gemm_op))
     .SetInferShapeFn(PD_INFER_SHAPE(GgInferShape))
     .SetInferDtypeFn(PD_INFER_DTYPE(GgInferDtype));
+
+// ---------------------------------------------------------------- round 2: fp16-pair tensor-core paths + rank preparation
+// Activations travel between these ops as FLOAT16 tensors holding (hi, lo') pairs ([rows, 2 * C], see include/p3d_b200.h);
+// STATUS is a 1-element INT32 tensor the kernels OR range-overflow bits into (checked by the caller once per frame).
+std::vector<paddle::Tensor> p3d_rows_to_h16_op(const paddle::Tensor &rows, const paddle::Tensor &num, const paddle::Tensor &status) {
+  P3D_CHECK_GPU(rows);
+  const int64_t cap = rows.shape()[0];
+  const int C = static_cast<int>(rows.shape()[1]);
+  auto out = paddle::empty({cap, 2 * C}, paddle::DataType::FLOAT16, paddle::GPUPlace());
+  P3D_CALL(p3d_rows_convert_h16(rows.data<float>(), 1, num.data<int>(), cap, C, out.data(), const_cast<int *>(status.data<int>()),
+                                rows.stream()));
+  return {out};
+}
+std::vector<std::vector<int64_t>> ToH16InferShape(std::vector<int64_t> r, std::vector<int64_t> n, std::vector<int64_t> s) {
+  return {{r[0], 2 * r[1]}};
+}
+std::vector<paddle::DataType> ToH16InferDtype(paddle::DataType r, paddle::DataType n, paddle::DataType s) {
+  return {paddle::DataType::FLOAT16};
+}
+PD_BUILD_OP(p3d_rows_to_h16)
+    .Inputs({"ROWS", "NUM", "STATUS"})
+    .Outputs({"OUT"})
+    .SetKernelFn(PD_KERNEL(p3d_rows_to_h16_op))
+    .SetInferShapeFn(PD_INFER_SHAPE(ToH16InferShape))
+    .SetInferDtypeFn(PD_INFER_DTYPE(ToH16InferDtype));
+
+// sparse conv (SubmConv3D / Conv3D + BatchNorm(eval) + add + ReLU, sparse_resnet.py:31-60,84-111) on fp16-pair rows.
+// WEIGHT is the packed image of p3d_sparse_conv_f16_pack_weights; RESIDUAL may be a 1-element tensor meaning "none";
+// want_f32 = 1 returns fp32 rows [cap, Cout] (last layer before to_dense), else fp16-pair rows [cap, 2 * Cout].
+std::vector<paddle::Tensor> p3d_sparse_conv_f16_op(const paddle::Tensor &in, const paddle::Tensor &nbr, const paddle::Tensor &num,
+                                                   const paddle::Tensor &weight, const paddle::Tensor &scale,
+                                                   const paddle::Tensor &shift, const paddle::Tensor &residual,
+                                                   const paddle::Tensor &status, const int cin, const int cout, const int relu,
+                                                   const int want_f32, const int max_splits) {
+  P3D_CHECK_GPU(in);
+  const int64_t cap = nbr.shape()[0];
+  const int K = static_cast<int>(nbr.shape()[1]);
+  auto out = want_f32 ? paddle::empty({cap, cout}, paddle::DataType::FLOAT32, paddle::GPUPlace())
+                      : paddle::empty({cap, 2 * cout}, paddle::DataType::FLOAT16, paddle::GPUPlace());
+  const size_t ws_bytes = p3d_sparse_conv_f16_workspace_bytes(cap, cout, max_splits);
+  // the ticket head of the workspace must be zero on first use: paddle::full, not empty
+  auto ws = paddle::full({static_cast<int64_t>(ws_bytes ? ws_bytes : 16)}, 0, paddle::DataType::UINT8, paddle::GPUPlace());
+  const void *res = residual.numel() > 1 ? residual.data() : nullptr;
+  P3D_CALL(p3d_sparse_conv_f16(in.data(), nbr.data<int>(), num.data<int>(), cap, K, cin, cout, weight.data(), scale.data<float>(),
+                               shift.data<float>(), res, relu, want_f32 ? out.data<float>() : nullptr,
+                               want_f32 ? nullptr : out.data(), ws_bytes ? ws.data<uint8_t>() : nullptr, ws_bytes, max_splits,
+                               const_cast<int *>(status.data<int>()), in.stream()));
+  return {out};
+}
+std::vector<std::vector<int64_t>> ScF16InferShape(std::vector<int64_t> in, std::vector<int64_t> nbr, std::vector<int64_t> num,
+                                                  std::vector<int64_t> w, std::vector<int64_t> sc, std::vector<int64_t> sh,
+                                                  std::vector<int64_t> res, std::vector<int64_t> st, const int &cin,
+                                                  const int &cout, const int &relu, const int &want_f32, const int &max_splits) {
+  return {{nbr[0], want_f32 ? static_cast<int64_t>(cout) : static_cast<int64_t>(2 * cout)}};
+}
+std::vector<paddle::DataType> ScF16InferDtype(paddle::DataType in, paddle::DataType nbr, paddle::DataType num, paddle::DataType w,
+                                              paddle::DataType sc, paddle::DataType sh, paddle::DataType res, paddle::DataType st) {
+  return {in};  // refined at run time by want_f32 (attrs are not visible to the dtype function of this API level)
+}
+PD_BUILD_OP(p3d_sparse_conv_f16)
+    .Inputs({"IN", "NBR", "NUM", "WEIGHT", "SCALE", "SHIFT", "RESIDUAL", "STATUS"})
+    .Outputs({"OUT"})
+    .Attrs({"cin: int", "cout: int", "relu: int", "want_f32: int", "max_splits: int"})
+    .SetKernelFn(PD_KERNEL(p3d_sparse_conv_f16_op))
+    .SetInferShapeFn(PD_INFER_SHAPE(ScF16InferShape))
+    .SetInferDtypeFn(PD_INFER_DTYPE(ScF16InferDtype));
+
+// dense Conv2D / Conv2DTranspose + BatchNorm2D(eval) + ReLU on pixel fp16-pair rows (second_backbone.py:72-120,
+// second_fpn.py:99-160, center_head.py:43-220).  IMAGE [B*H*W, 2*Cin] FLOAT16; WEIGHT = packed image
+// (p3d_dense_conv2d_f16_pack_weights per N tile).  Output rows have out_channels channels, this layer writes
+// [out_c0, out_c0 + cout) (channel concat of the neck for free).
+std::vector<paddle::Tensor> p3d_dense_conv2d_f16_op(const paddle::Tensor &image, const paddle::Tensor &weight,
+                                                    const paddle::Tensor &scale, const paddle::Tensor &shift,
+                                                    const paddle::Tensor &status, const std::vector<int> &bhwc, const int cout,
+                                                    const int n_tile, const int kernel, const int stride, const int pad,
+                                                    const int up, const int relu, const int out_channels, const int out_c0) {
+  P3D_CHECK_GPU(image);
+  const int B = bhwc[0], H = bhwc[1], W = bhwc[2], Cin = bhwc[3];
+  const int oH = up > 1 ? H * up : (H + 2 * pad - kernel) / stride + 1, oW = up > 1 ? W * up : (W + 2 * pad - kernel) / stride + 1;
+  auto out = paddle::empty({static_cast<int64_t>(B) * oH * oW, 2 * out_channels}, paddle::DataType::FLOAT16, paddle::GPUPlace());
+  const int k = up > 1 ? up : kernel, s = up > 1 ? up : stride;
+  P3D_CALL(p3d_dense_conv2d_f16(image.data(), B, H, W, Cin, weight.data(), cout, n_tile, k, k, s, up > 1 ? 0 : pad, up,
+                                scale.data<float>(), shift.data<float>(), relu, out.data(), out_channels, out_c0, nullptr, 0, 0,
+                                const_cast<int *>(status.data<int>()), image.stream()));
+  return {out};
+}
+std::vector<std::vector<int64_t>> DcF16InferShape(std::vector<int64_t> im, std::vector<int64_t> w, std::vector<int64_t> sc,
+                                                  std::vector<int64_t> sh, std::vector<int64_t> st, const std::vector<int> &bhwc,
+                                                  const int &cout, const int &n_tile, const int &kernel, const int &stride,
+                                                  const int &pad, const int &up, const int &relu, const int &out_channels,
+                                                  const int &out_c0) {
+  const int64_t oH = up > 1 ? bhwc[1] * up : (bhwc[1] + 2 * pad - kernel) / stride + 1;
+  const int64_t oW = up > 1 ? bhwc[2] * up : (bhwc[2] + 2 * pad - kernel) / stride + 1;
+  return {{bhwc[0] * oH * oW, 2 * static_cast<int64_t>(out_channels)}};
+}
+std::vector<paddle::DataType> DcF16InferDtype(paddle::DataType im, paddle::DataType w, paddle::DataType sc, paddle::DataType sh,
+                                              paddle::DataType st) {
+  return {paddle::DataType::FLOAT16};
+}
+PD_BUILD_OP(p3d_dense_conv2d_f16)
+    .Inputs({"IMAGE", "WEIGHT", "SCALE", "SHIFT", "STATUS"})
+    .Outputs({"OUT"})
+    .Attrs({"bhwc: std::vector<int>", "cout: int", "n_tile: int", "kernel: int", "stride: int", "pad: int", "up: int",
+            "relu: int", "out_channels: int", "out_c0: int"})
+    .SetKernelFn(PD_KERNEL(p3d_dense_conv2d_f16_op))
+    .SetInferShapeFn(PD_INFER_SHAPE(DcF16InferShape))
+    .SetInferDtypeFn(PD_INFER_DTYPE(DcF16InferDtype));
+
+// LSSViewTransformer.voxel_pooling_prepare_v2 (bevdet_transformer.py:230-274) as an op: COOR [B, N, D, H, W, 3] ->
+// five capacity-sized INT32 rank arrays + COUNTS {n_kept, n_intervals}; the Python wrapper slices them.
+std::vector<paddle::Tensor> p3d_bev_pool_prepare_op(const paddle::Tensor &coor, const std::vector<float> &lower,
+                                                    const std::vector<float> &interval, const std::vector<int> &grid_size) {
+  P3D_CHECK_GPU(coor);
+  const auto sh = coor.shape();
+  const int B = sh[0], N = sh[1], D = sh[2], H = sh[3], W = sh[4];
+  const int64_t n = static_cast<int64_t>(B) * N * D * H * W;
+  std::vector<paddle::Tensor> out;
+  for (int i = 0; i < 5; ++i) out.push_back(paddle::empty({n}, paddle::DataType::INT32, paddle::GPUPlace()));
+  out.push_back(paddle::empty({2}, paddle::DataType::INT32, paddle::GPUPlace()));
+  const size_t ws_bytes = p3d_bev_pool_prepare_workspace_bytes(n);
+  auto ws = workspace(ws_bytes);
+  P3D_CALL(p3d_bev_pool_prepare(coor.data<float>(), B, N, D, H, W, lower.data(), interval.data(), grid_size.data(),
+                                out[0].data<int>(), out[1].data<int>(), out[2].data<int>(), out[3].data<int>(), out[4].data<int>(),
+                                out[5].data<int>(), ws.data<uint8_t>(), ws_bytes, coor.stream()));
+  return out;
+}
+std::vector<std::vector<int64_t>> PrepInferShape(std::vector<int64_t> c, const std::vector<float> &lower,
+                                                 const std::vector<float> &interval, const std::vector<int> &grid_size) {
+  const int64_t n = c[0] * c[1] * c[2] * c[3] * c[4];
+  return {{n}, {n}, {n}, {n}, {n}, {2}};
+}
+std::vector<paddle::DataType> PrepInferDtype(paddle::DataType c) {
+  return {paddle::DataType::INT32, paddle::DataType::INT32, paddle::DataType::INT32, paddle::DataType::INT32,
+          paddle::DataType::INT32, paddle::DataType::INT32};
+}
+PD_BUILD_OP(p3d_bev_pool_prepare)
+    .Inputs({"COOR"})
+    .Outputs({"RANKS_BEV", "RANKS_DEPTH", "RANKS_FEAT", "INTERVAL_STARTS", "INTERVAL_LENGTHS", "COUNTS"})
+    .Attrs({"grid_lower_bound: std::vector<float>", "grid_interval: std::vector<float>", "grid_size: std::vector<int>"})
+    .SetKernelFn(PD_KERNEL(p3d_bev_pool_prepare_op))
+    .SetInferShapeFn(PD_INFER_SHAPE(PrepInferShape))
+    .SetInferDtypeFn(PD_INFER_DTYPE(PrepInferDtype));

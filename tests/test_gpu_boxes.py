@@ -244,3 +244,39 @@ def test_nms_callers_on_device(cuda, oracle_mod):
     a, c = synth.random_boxes(40, 7), synth.random_boxes(30, 8)
     iou = nms_utils.boxes_iou3d_gpu(_t(cuda, a), _t(cuda, c)).cpu().numpy()
     assert iou.shape == (40, 30) and (iou >= 0).all() and (iou <= 1 + 1e-5).all()
+
+
+def test_voxel_pooling_prepare_v2_on_device(cuda, oracle_mod):
+    """a-10 / f-3: frustum points -> sorted ranks + run lengths, bit-exact against the numpy restatement of
+    bevdet_transformer.py:230-274 (stable tie order), then chained into bev_pool_v2 (identical BEV tensor)."""
+    import torch
+    from paddle3d_b200.ops import bev_pool_v2 as bp
+    for grid, b in (((128, 128, 1), (-51.2, 51.2)), ((200, 200, 1), (-50.0, 50.0))):
+        d = synth.bev_pool_inputs(9, grid=grid, bounds=(b, b, (-5.0, 3.0)))
+        coor = d["coor"].copy()
+        coor[0, 0, 0, 0, :3] = [[np.nan, 0, 0], [1e30, 0, 0], [-0.3 * d["grid_interval"][0] + d["grid_lower_bound"][0], 0.0, 0.0]]
+        want = oracle_mod.voxel_pooling_prepare_v2(coor, d["grid_lower_bound"], d["grid_interval"], d["grid_size"])
+        prep = bp.voxel_pooling_prepare_v2(_t(cuda, coor), d["grid_lower_bound"], d["grid_interval"], d["grid_size"])
+        got = bp.trim(prep)
+        for g, w, name in zip(got, want, ("ranks_bev", "ranks_depth", "ranks_feat", "interval_starts", "interval_lengths")):
+            assert np.array_equal(g.cpu().numpy(), w), name
+        assert not prep[0][len(want[0]):].any() and not prep[4][len(want[3]):].any()  # capacity tails are zero
+        rb, rd, rf, st, ln = got
+        bev = bp.bev_pool_v2(_t(cuda, d["depth"]), _t(cuda, d["feat"]), rd, rf, rb, ln, st, d["bev_feat_shape"])
+        ref = oracle_mod.bev_pool_v2(d["depth"], d["feat"], want[1], want[2], want[0], want[4], want[3], d["bev_feat_shape"], use_fma=True)
+        assert np.array_equal(bev.cpu().numpy(), ref)
+    # nothing inside the grid -> the reference's five Nones
+    far = np.full((1, 1, 2, 2, 2, 3), 1e6, np.float32)
+    assert bp.trim(bp.voxel_pooling_prepare_v2(_t(cuda, far), [-50, -50, -5], [0.5, 0.5, 8], [200, 200, 1])) == (None,) * 5
+
+
+def test_bev_pool_round1_kernel_still_bit_exact(cuda, oracle_mod, monkeypatch):
+    """The float4-per-thread kernel (odd channel counts, C > 256) is still reachable and exact: C = 7 takes the scalar
+    path, C = 260 the float4 path."""
+    from paddle3d_b200.ops import bev_pool_v2
+    keys = ["depth", "feat", "ranks_depth", "ranks_feat", "ranks_bev", "interval_lengths", "interval_starts"]
+    for C_ in (7, 260):
+        d = synth.bev_pool_inputs(4, C=C_, D=12, H=8, W=10, grid=(32, 32, 1), bounds=((-20, 20), (-20, 20), (-5, 3)))
+        got = bev_pool_v2.bev_pool_v2(*[_t(cuda, d[k]) for k in keys], d["bev_feat_shape"])
+        want = oracle_mod.bev_pool_v2(*[d[k] for k in keys], d["bev_feat_shape"], use_fma=True)
+        assert np.array_equal(got.cpu().numpy(), want)

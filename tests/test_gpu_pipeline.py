@@ -95,3 +95,26 @@ def test_frame_with_dense_head(cuda, oracle_mod):
             assert np.abs(g.cpu().numpy() - w).max() <= 1e-4 * max(1.0, np.abs(w).max()), name
     assert int(out["status"].max().item()) == 0
     assert int(out["counts"][-1].item()) >= len(pipe.label_off)  # at least the one row per task the op always emits
+
+
+def test_deploy_predictor_matches_pipeline(cuda, tmp_path):
+    """deploy.Predictor: a .bin sweep with fewer points than the capacity gives the same detections as the
+    pipeline fed the same points (NaN padding rows are dropped by the voxelizer), and the result file has one line per
+    real detection."""
+    import torch
+    from paddle3d_b200 import deploy
+    pts = synth.lidar_cloud(synth.C3, 21, num_points=30000)
+    f = tmp_path / "sweep.bin"
+    pts.tofile(f)
+    p = deploy.preprocess(str(f), 5, False)
+    p = np.hstack([p, pts[:, 4:5]])  # keep the file's own lag column for this check
+    pred = deploy.Predictor(synth.C3, cuda, max_points=N_POINTS, seed=3, with_head=False)
+    b, l, s = pred.run(p)
+    ref = _pipe(cuda, 4)
+    full = np.full((N_POINTS, 5), np.nan, np.float32)
+    full[:len(p)] = p
+    rb, rs, rl = ref.infer(torch.from_numpy(full).pin_memory())
+    assert np.array_equal(b, rb.numpy()) and np.array_equal(l, rl.numpy()) and np.array_equal(s, rs.numpy())
+    out = tmp_path / "det.txt"
+    deploy.write_results(str(out), b, l, s)
+    assert len(out.read_text().splitlines()) == int((s >= 0).sum())

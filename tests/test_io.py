@@ -56,3 +56,24 @@ def test_reader_edge_cases(tmp_path):
         p3d_io.load_point_cloud(paths[0], 5, sweeps=sweeps, order=[0, 0, 1])
     with pytest.raises(ValueError):
         p3d_io.read_bin(paths[0], 7)  # 2500 floats are not a multiple of 7
+
+
+def test_deploy_preprocess_and_result_format(tmp_path):
+    """deploy.preprocess / parse_result against deploy/centerpoint/python/infer.py:86-104,139-160: column selection, the
+    zero time-lag column, the exact text of a 9-value and a 7-value detection line, fake rows (score -1) skipped."""
+    from paddle3d_b200 import deploy
+    rng = np.random.default_rng(0)
+    raw = rng.normal(size=(50, 5)).astype(np.float32)
+    f = tmp_path / "s.bin"
+    raw.tofile(f)
+    p = deploy.preprocess(str(f), 5, True)
+    assert p.shape == (50, 5) and np.array_equal(p[:, :4], raw[:, :4]) and not p[:, 4].any()
+    assert deploy.preprocess(str(f), 5, False).shape == (50, 4)
+    boxes = np.arange(18, dtype=np.float32).reshape(2, 9)
+    lines = deploy.format_result(boxes, np.array([3, 0]), np.array([0.5, -1.0], np.float32))
+    assert lines == ["Score: 0.5 Label: 3 Box(x_c, y_c, z_c, w, l, h, vec_x, vec_y, -rot): 0.0 1.0 2.0 3.0 4.0 5.0 6.0 7.0 8.0"]
+    l7 = deploy.format_result(boxes[:, :7], np.array([1, 2]), np.array([0.25, 0.75], np.float32))
+    assert l7[1] == "Score: 0.75 Label: 2 Box(x_c, y_c, z_c, w, l, h, -rot): 9.0 10.0 11.0 12.0 13.0 14.0 15.0"
+    out = tmp_path / "r.txt"
+    deploy.write_results(str(out), boxes, np.array([3, 0]), np.array([0.5, 0.9], np.float32))
+    assert len(out.read_text().splitlines()) == 2

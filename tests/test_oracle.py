@@ -211,3 +211,14 @@ def test_pillar_feature_net_oracle_vs_torch(oracle_mod):
     np.testing.assert_allclose(got, want, rtol=1e-5, atol=1e-6)
     pad = np.maximum((0 - mu) / np.sqrt(var + 1e-3) * g + b, 0)  # what a padding row contributes
     assert (got[npv < m] >= pad.astype(np.float32) - 1e-6).all()
+
+
+def test_prepare_restatement_matches_the_generator(oracle_mod):
+    """oracle.voxel_pooling_prepare_v2 (line-by-line restatement of bevdet_transformer.py:230-274) against the ranks the
+    synthetic-input generator builds the same way: two statements of the same algorithm must agree."""
+    from paddle3d_b200 import synth
+    d = synth.bev_pool_inputs(3, D=20, H=6, W=10, grid=(64, 64, 1), bounds=((-30, 30), (-30, 30), (-5, 3)))
+    got = oracle_mod.voxel_pooling_prepare_v2(d["coor"], d["grid_lower_bound"], d["grid_interval"], d["grid_size"])
+    for g, k in zip(got, ("ranks_bev", "ranks_depth", "ranks_feat", "interval_starts", "interval_lengths")):
+        assert np.array_equal(g, d[k]), k
+    assert (np.diff(got[0]) >= 0).all() and got[4].sum() == len(got[0])

@@ -18,7 +18,8 @@ import numpy as np  # noqa: E402
 import torch  # noqa: E402
 
 from paddle3d_b200 import synth  # noqa: E402
-from paddle3d_b200.ops import bev_pool_v2, centerpoint_postprocess, iou3d_nms, pillar_scatter, voxelize  # noqa: E402
+from paddle3d_b200.ops import (bev_pool_v2, centerpoint_postprocess, iou3d_nms, pillar_encoder, pillar_scatter,  # noqa: E402
+                               voxelize)
 
 
 def timed(fn, iters, flush):
@@ -80,10 +81,10 @@ def main():
                "fused VoxelMean front end (no padded tensor)")
     # PillarScatter — C2: [nv, 64] -> [1, 64, 496, 432]
     cfg = synth.C2
-    import oracle
-    v, c, n, nv = oracle.hard_voxelize(synth.uniform_cloud(cfg, 1), cfg["voxel_size"], cfg["point_cloud_range"], 4, 40000)
-    k = int(nv[0])
-    coors = torch.from_numpy(np.concatenate([np.zeros((k, 1), np.int32), c[:k]], 1)).to(dev)
+    _, c_dev, _, nv_dev = voxelize.hard_voxelize(torch.from_numpy(synth.uniform_cloud(cfg, 1)).to(dev), cfg["voxel_size"],
+                                                 cfg["point_cloud_range"], 4, 40000)
+    k = int(nv_dev[0].item())
+    coors = torch.cat([torch.zeros((k, 1), dtype=torch.int32, device=dev), c_dev[:k]], 1).contiguous()
     feats = torch.randn((k, 64), device=dev)
     report("scatter:pillar_scatter", "C2 nv=%d C=64 496x432" % k, 4 * k * 64 + 16 * k + 4 * 64 * 496 * 432,
            lambda: pillar_scatter.pillar_scatter(feats, coors, 1, 496, 432), "memset map + scat_map + scat_write")
@@ -103,6 +104,41 @@ def main():
         nbytes = 12 * npts + 4 * npts + 4 * d["feat"].size + 8 * nint + 4 * int(np.prod(d["bev_feat_shape"]))
         report("bev_pool:bev_pool_v2", "C4 grid %dx%d n_pts=%d n_int=%d C=80" % (grid[0], grid[1], npts, nint), nbytes,
                lambda: bev_pool_v2.bev_pool_v2(*t, d["bev_feat_shape"]), "memset + bev_fwd")
+    # BASELINE.json config 4, camera branch: rank preparation (on the device, every frame) + bev_pool_v2 onto 200 x 200
+    d = synth.bev_pool_inputs(5, grid=(200, 200, 1), bounds=((-50.0, 50.0), (-50.0, 50.0), (-5.0, 3.0)))
+    coor_dev, depth_dev, feat_dev = [torch.from_numpy(d[kk]).to(dev) for kk in ("coor", "depth", "feat")]
+    n_all = d["coor"].size // 3
+    npts, nint = len(d["ranks_bev"]), len(d["interval_starts"])
+
+    def camera_branch():
+        rb, rd, rf, st_, ln, counts = bev_pool_v2.voxel_pooling_prepare_v2(coor_dev, d["grid_lower_bound"], d["grid_interval"],
+                                                                            d["grid_size"])
+        # capacity-sized arrays + the known interval count of this rig (a deployment reads counts once per calibration)
+        return bev_pool_v2.bev_pool_v2(depth_dev, feat_dev, rd, rf, rb, ln[:nint], st_[:nint], d["bev_feat_shape"])
+    report("c4:camera_branch prepare+bev_pool", "6 cams 16x44x118 -> 200x200x80, n_pts=%d kept=%d n_int=%d" % (n_all, npts, nint),
+           12 * n_all + 20 * npts + 4 * npts + 4 * d["feat"].size + 8 * nint + 4 * int(np.prod(d["bev_feat_shape"])), camera_branch,
+           "prep_rank + radix sort + gather + scan + starts + lengths + memset + bev_fwd_warp")
+    report("c4:prepare only", "n_pts=%d" % n_all, 12 * n_all + 20 * npts,
+           lambda: bev_pool_v2.voxel_pooling_prepare_v2(coor_dev, d["grid_lower_bound"], d["grid_interval"], d["grid_size"]))
+    # configs 2 and 4 (LiDAR branch): hard_voxelize -> PillarFeatureNet -> PointPillarsScatter
+    for cfg, hw, label in ((synth.C2, (496, 432), "c2:pointpillars voxelize+PFN+scatter"),
+                           (synth.C4_LIDAR, (400, 400), "c4:lidar_branch voxelize+PFN+scatter")):
+        pts = torch.from_numpy(synth.lidar_cloud(cfg, 0)).to(dev)
+        N, F, P, V = pts.shape[0], pts.shape[1], cfg["max_points"], cfg["max_voxels"]
+        rng = np.random.default_rng(1)
+        w = torch.from_numpy((rng.normal(size=(F + 5, 64)) * 0.3).astype(np.float32)).to(dev)
+        g_, b_, mu, var = np.ones(64), np.zeros(64), np.zeros(64), np.ones(64)
+        folded = pillar_encoder.fold_bn(g_, b_, mu, var, 1e-3, dev)
+
+        def chain():
+            vox, co, npv, nv = voxelize.hard_voxelize(pts, cfg["voxel_size"], cfg["point_cloud_range"], P, V)
+            coors4 = torch.cat([torch.zeros((V, 1), dtype=torch.int32, device=dev), co], 1)
+            f = pillar_encoder.pillar_feature_net(vox, npv, coors4, w, g_, b_, mu, var, 1e-3, cfg["voxel_size"],
+                                                  cfg["point_cloud_range"], num_voxels=nv, folded=folded)
+            return pillar_scatter.pillar_scatter(f, coors4, 1, hw[0], hw[1], nv)
+        nbytes = 4 * N * F + 2 * (4 * V * P * F + 16 * V) + 4 * V * 64 * 2 + 4 * 64 * hw[0] * hw[1]
+        report(label, "%s: %d pts, V=%d P=%d -> [1,64,%d,%d]" % (cfg["name"], N, V, P, hw[0], hw[1]), nbytes, chain,
+               "hard_voxelize (5 launches) + cat + PFN + memset + scat_map + scat_write")
     # NMS — 1000 boxes (latency/ALU bound: report pairs/s instead of an HBM fraction)
     boxes = torch.from_numpy(synth.random_boxes(1000, 3)).to(dev)
     report("nms:nms_gpu", "1000 boxes thr 0.2", 28 * 1000 + 8 * 1000 * 16,
