@@ -40,6 +40,7 @@ WORKLOAD = ("CenterPoint-voxel nuScenes-shape frame, 300k x 5 points, 1440x1440x
             "-> SparseResNet3D (21 sparse convs) -> dense BEV [1,256,180,180] -> %s -> centerpoint_postprocess (6 tasks)")
 HEAD_ON = "SecondBackbone + SecondFPN + CenterHead (2 x 6 + 2 + 1 + 36 + 36 convs, 234 GFLOP)"
 HEAD_OFF = "resident synthetic head tensors (dense RPN/head skipped: --no-head)"
+BN_GAIN = 6.0 ** 0.5  # seeded weights with BatchNorm gamma = sqrt(6): activations stay O(1) through the 21 + 54 convs
 POOL = 32  # distinct frames cycled through: 32 x 6 MB = 192 MB of inputs > 126 MB L2
 
 
@@ -139,11 +140,12 @@ def build_cpu_frame(cfg, with_head, weights=None, dense_weights=None, head=None)
         class _W:
             pass
         w = _W()
-        w.net = SparseResNet3D(cfg["point_dim"], cfg["voxel_size"], cfg["point_cloud_range"]).init_weight(seed=0, device="cpu")
+        w.net = SparseResNet3D(cfg["point_dim"], cfg["voxel_size"], cfg["point_cloud_range"]).init_weight(seed=0, device="cpu",
+                                                                                                         bn_gain=BN_GAIN)
         weights = CenterPointHotPath.export_weights_numpy(w)
     if with_head and dense_weights is None:
         from paddle3d_b200.dense_head import DenseRPNHead
-        dense_weights = DenseRPNHead(in_channels=256).init_weight(seed=1, device=None).export_numpy()
+        dense_weights = DenseRPNHead(in_channels=256).init_weight(seed=1, device=None, bn_gain=BN_GAIN).export_numpy()
     if head is None:
         head = synth.centerpoint_head_outputs(0)
     return CpuFrame(cfg, weights, head, synth.CENTERPOINT_TEST_CFG, synth.label_offsets(),
@@ -235,17 +237,6 @@ def ncu_dram_bytes(path_name):
         return total
     except (ValueError, KeyError, IndexError, OSError):
         return None  # a malformed capture must not take the benchmark down
-
-
-def count_graph_nodes(dot_path):
-    """Nodes of the captured frame graph (kernels, plus the few memset / memcpy nodes torch adds) from its DOT dump."""
-    import re
-    try:
-        txt = open(dot_path).read()
-    except OSError:
-        return None
-    nodes = set(re.findall(r'"?(graph_\w+?_node_\d+)"?\s*\[', txt))
-    return len(nodes) or None
 
 
 def dense_flops(net, H, W):
@@ -439,7 +430,8 @@ def main():
     precision = {"tf32x3": sp.TF32X3, "tf32x3_split": sp.TF32X3_SPLIT, "tf32x3_tma": sp.TF32X3_TMA, "fp32": sp.FP32,
                  "f16x3": sp.F16X3}[args.precision]
     caps = [int(x) for x in os.environ["P3D_LEVEL_CAPS"].split(",")] if os.environ.get("P3D_LEVEL_CAPS") else None
-    pipe = CenterPointHotPath(cfg, dev, precision=precision, seed=0, level_caps=caps, with_head=with_head)
+    pipe = CenterPointHotPath(cfg, dev, precision=precision, seed=0, level_caps=caps, with_head=with_head, keep_bev=False,
+                              bn_gain=BN_GAIN)
     if world > 1:  # weights only: one broadcast over NVLink at start, no per-frame collective
         from paddle3d_b200.sharding import broadcast_weights
         broadcast_weights(pipe.net, 0)
@@ -449,12 +441,8 @@ def main():
     host_frames = [torch.from_numpy(f).pin_memory() for f in frames]
     pipe.calibrate_head(dev_frames[0])   # random-init heat maps -> ~1.4 % of cells above the score threshold
     pipe.points.copy_(dev_frames[0])
-    dot = os.path.join("/tmp", "p3d_frame_graph_%d.dot" % os.getpid())
-    pipe.capture(dump_path=dot if rank == 0 else None)
-    graph_nodes = count_graph_nodes(dot) if rank == 0 else None
-    if rank == 0 and os.path.isdir(os.path.join(ROOT, "gpurun_out")) and os.path.exists(dot):
-        import shutil
-        shutil.copy(dot, os.path.join(ROOT, "gpurun_out", "frame_graph.dot"))
+    pipe.capture(count_nodes=rank == 0)
+    graph_nodes = pipe.graph_nodes["kernel"] if (rank == 0 and pipe.graph_nodes) else None
     st = pipe.stream
     m = measure(pipe, dev_frames, host_frames, args, world, dist, True, local)
 
@@ -463,7 +451,8 @@ def main():
     if not args.no_second_geometry:
         ogeo = "01" if args.geometry == "0075" else "0075"
         ocfg = synth.C3_01 if ogeo == "01" else synth.C3
-        opipe = CenterPointHotPath(ocfg, dev, precision=precision, seed=0, level_caps=caps, with_head=with_head)
+        opipe = CenterPointHotPath(ocfg, dev, precision=precision, seed=0, level_caps=caps, with_head=with_head, keep_bev=False,
+                                   bn_gain=BN_GAIN)
         oframes = frame_pool(ocfg, 8, seed0=rank * 100, base=2)
         odev = [torch.from_numpy(f).to(dev) for f in oframes]
         ohost = [torch.from_numpy(f).pin_memory() for f in oframes]
@@ -505,10 +494,16 @@ def main():
                 x, _ = pipe.net.forward_sparse(mean, coors, 1, num=nv)
                 x.values()
                 ev[2].record(st)
-                bev = x.to_dense_bev()
-                pipe.net.join()
-                ev[3].record(st)
-                h = pipe.dense(bev) if pipe.dense is not None else pipe.head
+                if pipe.keep_bev:
+                    bev = x.to_dense_bev()
+                    pipe.net.join()
+                    ev[3].record(st)
+                    h = pipe.dense(bev) if pipe.dense is not None else pipe.head
+                else:
+                    bev16 = x.to_pixel_h16()
+                    pipe.net.join()
+                    ev[3].record(st)
+                    h = pipe.dense.forward_h16(*bev16)
                 ev[4].record(st)
                 tc = pipe.test_cfg
                 cpp.centerpoint_postprocess_device(h["hm"], h["reg"], h["height"], h["dim"], h["vel"], h["rot"],
@@ -561,9 +556,14 @@ def main():
                                    "row, profiles/r02_f16_probe.md), not by the tensor pipe"}
         dense_roof = None
         if pipe.dense is not None:
-            bev_t = pipe.out["bev"]
-            ms_dense = graph_time_ms(lambda: pipe.dense(bev_t), st, 3)
-            fl = dense_flops(pipe.dense, bev_t.shape[2], bev_t.shape[3])
+            if pipe.out["bev_h16"] is not None:
+                rows_t, shp = pipe.out["bev_h16"]
+                ms_dense = graph_time_ms(lambda: pipe.dense.forward_h16(rows_t, shp), st, 3)
+                fl = dense_flops(pipe.dense, shp[1], shp[2])
+            else:
+                bev_t = pipe.out["bev"]
+                ms_dense = graph_time_ms(lambda: pipe.dense(bev_t), st, 3)
+                fl = dense_flops(pipe.dense, bev_t.shape[2], bev_t.shape[3])
             ach = fl / (ms_dense * 1e-3) / 1e12
             dense_roof = {"bound": "tensor", "kernel": "dcf::dense_conv_f16_kernel (RPN + neck + CenterHead: 16 + 1 + 1 launches)",
                           "achieved": ach, "peak": bf16_peak, "unit": "TFLOP/s", "frac": ach / bf16_peak,
@@ -594,15 +594,20 @@ def main():
             # cross-check while we are here: GPU frame vs CPU frame on the same full-size input
             got = pipe.infer(host_frames[0])
             chk = {"num_voxels_equal": nvox == r["num_voxels"], "boxes_gpu": int(len(got[2])), "boxes_cpu": int(len(r["labels"]))}
-            chk["bev"] = rel_errors(pipe.out["bev"].cpu().numpy(), r["bev"])
+            bev_gpu = pipe.bev_nchw()
+            chk["bev"] = rel_errors(bev_gpu.cpu().numpy(), r["bev"])
             if r["head"] is not None:
-                gh = pipe.dense(pipe.out["bev"])
+                gh = pipe.dense(bev_gpu)
                 torch.cuda.synchronize()
-                worst = 0.0
+                worst, worst_spread = 0.0, 0.0
                 for name in r["head"]:
                     for g, wv in zip(gh[name], r["head"][name]):
-                        worst = max(worst, float(np.abs(g.cpu().numpy() - wv).max() / max(1.0, np.abs(wv).max())))
+                        err = float(np.abs(g.cpu().numpy() - wv).max())
+                        worst = max(worst, err / max(1.0, float(np.abs(wv).max())))
+                        worst_spread = max(worst_spread, err / max(1e-30, float(wv.max() - wv.min())))
                 chk["head_max_abs_err_over_range"] = worst
+                chk["head_max_abs_err_over_spread"] = worst_spread  # error relative to how much the map actually varies
+                chk["bev_abs_max"] = float(np.abs(r["bev"]).max())
             if len(got[2]) == len(r["labels"]):
                 chk["labels_equal"] = bool(np.array_equal(got[2].numpy(), r["labels"]))
             extra["frame0_check"] = chk
@@ -626,7 +631,8 @@ def main():
                         "sync_value": m["e2e_sync_value"] if world == 1 else None},
                 "gpu_launches": per_frame_launches * args.steps,
                 "gpu_launches_per_step": per_frame_launches,
-                "gpu_launches_source": "nodes of the captured CUDA graph (cudaGraphDebugDotPrint)" if graph_nodes else "estimate",
+                "gpu_launches_source": ("kernel nodes of the captured CUDA graph (cudaGraphGetNodes); all node types: %s" % pipe.graph_nodes)
+                if graph_nodes else "estimate",
                 "clocks": m["clocks"], "wall_ms_per_step": m["wall_ms_per_step"]}
         if other is not None:
             ogeo, om, oargs, onv = other

@@ -264,6 +264,14 @@ int p3d_sparse_conv_gather_gemm_split_tma(const float *in_split, int64_t n_in_ro
  *                                      bytes whose first align_up(tiles * 4) bytes (tickets) must be ZERO on first use
  *                                      (the kernel leaves them zero); workspace NULL or max_splits <= 1: no split.
  * ------------------------------------------------------------------------------------------- */
+/* fp16-pair plumbing around the tensor-core layers: the 5-channel input layer emitting pair rows directly, and the last
+ * level's rows scattered straight into the pixel H16 image [batch, ny, nx][D * C] the dense RPN reads (the fp16-pair form
+ * of to_dense + transpose + reshape, sparse_resnet.py:202-206; duplicates impossible: sites are unique). */
+int p3d_sparse_conv_small_cin_h16(const float *in, const int32_t *nbr, const int32_t *n_out_dev, int64_t n_out_cap, int K,
+                                  int Cin, int Cout, const float *weight, const float *scale, const float *shift, int relu,
+                                  float *out_f32, void *out_h16, int32_t *status_dev, p3d_stream_t stream);
+int p3d_sparse_rows_to_pixel_h16(const void *rows_h16, const int32_t *coords, const int32_t *n_dev, int n_cap, int C,
+                                 int batch, int D, int ny, int nx, void *out_pixel_h16, p3d_stream_t stream);
 size_t p3d_sparse_conv_f16_packed_weight_bytes(int K, int Cin, int Cout);
 int p3d_sparse_conv_f16_pack_weights(const float *weight, int K, int Cin, int Cout, void *packed, int32_t *status_dev,
                                      p3d_stream_t stream);

@@ -83,10 +83,45 @@ __global__ void __launch_bounds__(256) scat_write_kernel(const float *__restrict
   }
 }
 
+// Sparse rows (fp16-pair H16 rows of C channels, C % 32 == 0) -> pixel H16 image [batch, ny, nx][D * C channels]: the
+// fp16-pair form of SparseResNet3D's to_dense + transpose + reshape (sparse_resnet.py:202-206, channel = z * C + c) that
+// the dense RPN consumes directly (no fp32 NCHW tensor, no layout conversion pass).  One warp copies one row (4 * C bytes).
+__global__ void __launch_bounds__(256) rows_to_pixel_h16_kernel(const uint4 *__restrict__ rows, const int32_t *__restrict__ coords,
+                                                                const int32_t *__restrict__ n_dev, int n_cap, int C, int batch,
+                                                                int D, int ny, int nx, uint4 *__restrict__ out) {
+  const int n = n_dev ? min(n_dev[0], n_cap) : n_cap;
+  const int r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (r >= n) return;
+  const int4 c = *reinterpret_cast<const int4 *>(coords + static_cast<size_t>(r) * 4);
+  if (c.x < 0 || c.x >= batch || c.y < 0 || c.y >= D || c.z < 0 || c.z >= ny || c.w < 0 || c.w >= nx) return;
+  const int q_row = C / 4;  // uint4 per row (4 * C bytes)
+  uint4 *dst = out + ((static_cast<size_t>(c.x) * ny + c.z) * nx + c.w) * (static_cast<size_t>(D) * q_row) + static_cast<size_t>(c.y) * q_row;
+  const uint4 *src = rows + static_cast<size_t>(r) * q_row;
+  for (int q = lane; q < q_row; q += 32) dst[q] = __ldg(src + q);
+}
+
 }  // namespace
 }  // namespace p3d
 
 using namespace p3d;
+
+extern "C" int p3d_sparse_rows_to_pixel_h16(const void *rows_h16, const int32_t *coords, const int32_t *n_dev, int n_cap, int C,
+                                            int batch, int D, int ny, int nx, void *out_pixel_h16, p3d_stream_t stream) {
+  if (n_cap < 0 || C < 32 || C % 32 || batch < 1 || D < 1 || ny < 1 || nx < 1 || !out_pixel_h16 || (n_cap && (!rows_h16 || !coords)))
+    return P3D_ERR_INVALID_ARG;
+  if ((reinterpret_cast<uintptr_t>(rows_h16) & 15) || (reinterpret_cast<uintptr_t>(coords) & 15) ||
+      (reinterpret_cast<uintptr_t>(out_pixel_h16) & 15))
+    return P3D_ERR_INVALID_ARG;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const size_t bytes = static_cast<size_t>(batch) * ny * nx * D * C * 4;
+  P3D_CUDA_CHECK(cudaMemsetAsync(out_pixel_h16, 0, bytes, st));  // (hi, lo') = (0, 0) is the value 0
+  if (n_cap > 0) {
+    rows_to_pixel_h16_kernel<<<div_up(static_cast<long long>(n_cap) * 32, 256), 256, 0, st>>>(
+        static_cast<const uint4 *>(rows_h16), coords, n_dev, n_cap, C, batch, D, ny, nx, static_cast<uint4 *>(out_pixel_h16));
+    P3D_LAUNCH_CHECK();
+  }
+  return P3D_OK;
+}
 
 extern "C" size_t p3d_scatter_dense_workspace_bytes(int batch, int D, int ny, int nx) {
   if (batch < 1 || D < 1 || ny < 1 || nx < 1) return 0;

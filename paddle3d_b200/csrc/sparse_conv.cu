@@ -17,6 +17,8 @@
 //
 // This file holds the fp32 CUDA-core GEMM path (exact fp32 FMA accumulation, used for parity and
 // for the 5-channel input layer); the tcgen05 3xTF32 path lives in sparse_conv_tc.cu.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace p3d {
@@ -296,7 +298,10 @@ __global__ void __launch_bounds__(128) small_cin_kernel(const float *__restrict_
                                                         int Cin, const float *__restrict__ weight,
                                                         const float *__restrict__ scale, const float *__restrict__ shift,
                                                         const float *__restrict__ residual, int relu,
-                                                        float *__restrict__ out) {
+                                                        float *__restrict__ out, __half *__restrict__ out_h16,
+                                                        int32_t *__restrict__ status) {
+  // out_h16 (optional): the rows also (or only) as fp16 (hi, lo') pairs [n][hi COUT | lo' COUT] for the fp16-pair
+  // tensor-core layers that follow (csrc/sparse_conv_f16.cu): saves the separate conversion pass
   extern __shared__ float s_w[];  // [K][Cin][COUT]
   const long long n = n_out_dev ? min(static_cast<long long>(n_out_dev[0]), n_cap) : n_cap;
   if (static_cast<long long>(blockIdx.x) * blockDim.x >= n) return;
@@ -336,7 +341,7 @@ __global__ void __launch_bounds__(128) small_cin_kernel(const float *__restrict_
       }
     }
   }
-  float *o = out + row * COUT;
+  bool ovf = false;
 #pragma unroll
   for (int c = 0; c < COUT; ++c) {
     float v = acc[c];
@@ -344,7 +349,38 @@ __global__ void __launch_bounds__(128) small_cin_kernel(const float *__restrict_
     if (shift) v = v + shift[c];
     if (residual) v = v + residual[row * COUT + c];
     if (relu) v = fmaxf(v, 0.f);
-    o[c] = v;
+    acc[c] = v;
+  }
+  if (out) {
+    float4 *o = reinterpret_cast<float4 *>(out + row * COUT);
+#pragma unroll
+    for (int c = 0; c < COUT; c += 4) o[c / 4] = make_float4(acc[c], acc[c + 1], acc[c + 2], acc[c + 3]);
+  }
+  if (out_h16) {
+    uint32_t hw[COUT / 2], lw[COUT / 2];
+#pragma unroll
+    for (int c = 0; c < COUT; c += 2) {
+      float x0 = acc[c], x1 = acc[c + 1];
+      if (fabsf(x0) > 65504.f) {
+        ovf = true;
+        x0 = copysignf(65504.f, x0);
+      }
+      if (fabsf(x1) > 65504.f) {
+        ovf = true;
+        x1 = copysignf(65504.f, x1);
+      }
+      const __half h0 = __float2half_rn(x0), h1 = __float2half_rn(x1);
+      const __half l0 = __float2half_rn((x0 - __half2float(h0)) * 2048.0f), l1 = __float2half_rn((x1 - __half2float(h1)) * 2048.0f);
+      const __half2 hh = __halves2half2(h0, h1), ll = __halves2half2(l0, l1);
+      hw[c / 2] = *reinterpret_cast<const uint32_t *>(&hh);
+      lw[c / 2] = *reinterpret_cast<const uint32_t *>(&ll);
+    }
+    uint4 *o = reinterpret_cast<uint4 *>(out_h16 + row * 2 * COUT);  // [hi COUT | lo' COUT] (COUT = 16 or 32: one group)
+#pragma unroll
+    for (int q = 0; q < COUT / 8; ++q) o[q] = make_uint4(hw[4 * q], hw[4 * q + 1], hw[4 * q + 2], hw[4 * q + 3]);
+#pragma unroll
+    for (int q = 0; q < COUT / 8; ++q) o[COUT / 8 + q] = make_uint4(lw[4 * q], lw[4 * q + 1], lw[4 * q + 2], lw[4 * q + 3]);
+    if (ovf && status) atomicOr(status, 1);
   }
 }
 
@@ -476,10 +512,10 @@ extern "C" int p3d_sparse_conv_gather_gemm_fp32(const float *in, const int32_t *
     const size_t sw = static_cast<size_t>(K) * Cin * Cout * sizeof(float);
     if (Cout == 16)
       small_cin_kernel<16><<<div_up(n_out_cap, 128), 128, sw, static_cast<cudaStream_t>(stream)>>>(
-          in, nbr, n_out_dev, n_out_cap, K, Cin, weight, scale, shift, residual, relu, out);
+          in, nbr, n_out_dev, n_out_cap, K, Cin, weight, scale, shift, residual, relu, out, nullptr, nullptr);
     else
       small_cin_kernel<32><<<div_up(n_out_cap, 128), 128, sw, static_cast<cudaStream_t>(stream)>>>(
-          in, nbr, n_out_dev, n_out_cap, K, Cin, weight, scale, shift, residual, relu, out);
+          in, nbr, n_out_dev, n_out_cap, K, Cin, weight, scale, shift, residual, relu, out, nullptr, nullptr);
     P3D_LAUNCH_CHECK();
     return P3D_OK;
   }
@@ -488,6 +524,28 @@ extern "C" int p3d_sparse_conv_gather_gemm_fp32(const float *in, const int32_t *
   dim3 grid(div_up(n_out_cap, TM), div_up(Cout, TN));
   gather_gemm_fp32_kernel<<<grid, 256, smem, static_cast<cudaStream_t>(stream)>>>(
       in, nbr, n_out_dev, n_out_cap, K, Cin, Cout, weight, scale, shift, residual, relu, out);
+  P3D_LAUNCH_CHECK();
+  return P3D_OK;
+}
+
+// The few-input-channel layer (5 -> 16 input conv) with fp16-pair output rows for the tensor-core layers behind it:
+// out_f32 and / or out_h16 ([n][hi Cout | lo' Cout] halfs) may be given; exact fp32 FMA chain as p3d_sparse_conv_gather_gemm.
+extern "C" int p3d_sparse_conv_small_cin_h16(const float *in, const int32_t *nbr, const int32_t *n_out_dev, int64_t n_out_cap,
+                                             int K, int Cin, int Cout, const float *weight, const float *scale,
+                                             const float *shift, int relu, float *out_f32, void *out_h16,
+                                             int32_t *status_dev, p3d_stream_t stream) {
+  if (n_out_cap < 0 || K < 1 || !weight || (!out_f32 && !out_h16) || (n_out_cap && (!in || !nbr))) return P3D_ERR_INVALID_ARG;
+  if (n_out_cap == 0) return P3D_OK;
+  if (!(Cin <= 8 && (Cout == 16 || Cout == 32) && static_cast<size_t>(K) * Cin * Cout * 4 <= 40 * 1024)) return P3D_ERR_UNSUPPORTED;
+  if ((reinterpret_cast<uintptr_t>(out_f32) & 15) || (reinterpret_cast<uintptr_t>(out_h16) & 15)) return P3D_ERR_INVALID_ARG;
+  const size_t sw = static_cast<size_t>(K) * Cin * Cout * sizeof(float);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (Cout == 16)
+    small_cin_kernel<16><<<div_up(n_out_cap, 128), 128, sw, st>>>(in, nbr, n_out_dev, n_out_cap, K, Cin, weight, scale, shift, nullptr,
+                                                                  relu, out_f32, static_cast<__half *>(out_h16), status_dev);
+  else
+    small_cin_kernel<32><<<div_up(n_out_cap, 128), 128, sw, st>>>(in, nbr, n_out_dev, n_out_cap, K, Cin, weight, scale, shift, nullptr,
+                                                                  relu, out_f32, static_cast<__half *>(out_h16), status_dev);
   P3D_LAUNCH_CHECK();
   return P3D_OK;
 }

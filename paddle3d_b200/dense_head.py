@@ -26,7 +26,7 @@ class _Conv:
         self.np = None
         self.dev = None
 
-    def init(self, rng, device=None, randomize_bn=False, bias_value=None):
+    def init(self, rng, device=None, randomize_bn=False, bias_value=None, bn_gain=1.0):
         """Seeded parameters (numpy); with a device also the packed tensor-core image and the folded epilogue."""
         cin, cout, k = self.cin, self.cout, self.k
         bound = 1.0 / np.sqrt(cin * k * k)  # build_conv_layer "uniform" (second_backbone.py:43-48)
@@ -43,6 +43,7 @@ class _Conv:
                 m, v = rng.uniform(-0.1, 0.1, cout), rng.uniform(0.5, 1.5, cout)
             else:
                 g, bt, m, v = np.ones(cout), np.zeros(cout), np.zeros(cout), np.ones(cout)
+            g = g * bn_gain
             p["bn"] = dict(gamma=g.astype(np.float32), beta=bt.astype(np.float32), mean=m.astype(np.float32),
                            var=v.astype(np.float32), eps=self.bn_eps)
         self.np = p
@@ -79,8 +80,9 @@ class _Conv:
 class DenseRPNHead:
     def __init__(self, in_channels=256, out_channels=(128, 256), layer_nums=(5, 5), downsample_strides=(1, 2),
                  fpn_out_channels=(256, 256), upsample_strides=(1, 2), tasks=(1, 2, 2, 1, 2, 2), share_conv_channel=64,
-                 f16=True, with_velocity=True):
+                 f16=True, with_velocity=True, bev_depth=2):
         self.tasks = list(tasks)
+        self.in_channels, self.bev_depth = in_channels, bev_depth
         self.num_classes = list(tasks)        # CenterHead.num_classes (center_head.py:64)
         self.with_velocity = with_velocity    # 'vel' in common_heads (center_head.py:77)
         self.f16 = f16
@@ -116,16 +118,30 @@ class DenseRPNHead:
                 out += [a, b]
         return out
 
-    def init_weight(self, seed=0, device="cuda", randomize_bn=False):
-        """device=None: numpy parameters only (enough for export_numpy / the CPU arm)."""
+    def init_weight(self, seed=0, device="cuda", randomize_bn=False, bn_gain=1.0):
+        """device=None: numpy parameters only (enough for export_numpy / the CPU arm).  bn_gain multiplies every BatchNorm
+        gamma (sqrt(6) keeps the activations O(1) through the stack, see sparse_nn.BatchNorm.init_parameters)."""
         rng = np.random.default_rng(seed)
         hm_finals = {id(b) for hs in self.heads for name, _, b in hs if name == "hm"}
         finals = {id(b) for hs in self.heads for _, _, b in hs}
         for c in self.all_convs():  # hm bias = -2.19 (center_head.py:113-117)
             # the 1-3 channel output convs have no tensor-core image in f16 mode: they run grouped on the CUDA cores
             dev = None if (self.f16 and id(c) in finals) else device
-            c.init(rng, dev, randomize_bn, bias_value=-2.19 if id(c) in hm_finals else None)
+            c.init(rng, dev, randomize_bn, bias_value=-2.19 if id(c) in hm_finals else None, bn_gain=bn_gain)
         self._batched = None
+        self._first_zc = None
+        if self.f16 and device is not None and self.in_channels % self.bev_depth == 0:
+            # second image of the first conv for BEV tensors that arrive as pixel fp16-pair rows straight from the sparse
+            # rows (SparseCooTensor.to_pixel_h16): there a pixel's channels are ordered (z, c) = z * C + c, while the
+            # reference's to_dense + transpose + reshape (sparse_resnet.py:202-206) orders them (c, z) = c * D + z.  The
+            # input-channel axis of the weights is permuted once here instead of permuting activations every frame.
+            c0 = self.blocks[0][0]
+            D, C = self.bev_depth, self.in_channels // self.bev_depth
+            perm = np.asarray([c * D + z for z in range(D) for c in range(C)])
+            zc = _Conv(c0.cin, c0.cout, c0.k, c0.stride, c0.padding, bias=c0.has_bias, bn_eps=c0.bn_eps, relu=c0.relu, f16=True)
+            zc.np = dict(c0.np, weight=np.ascontiguousarray(c0.np["weight"][:, perm]))
+            zc.dev = dict(c0.dev, packed=dc.pack_conv_weight_f16(torch.from_numpy(zc.np["weight"]).to(device), zc.n_tile))
+            self._first_zc = zc
         return self
 
     def export_numpy(self):
@@ -133,13 +149,24 @@ class DenseRPNHead:
                     shared=self.shared.np, heads=[[(n, a.np, b.np) for n, a, b in hs] for hs in self.heads])
 
     # ---- RPN + neck + shared conv: bev [B, C, H, W] fp32 -> (pixel rows of the shared feature map, its shape)
-    def _trunk(self, bev):
-        b, c, h, w = bev.shape
-        x = dc.nchw_to_pixel_h16(bev) if self.f16 else dc.nchw_to_pixel_split(bev)
-        shape = (b, h, w, c)
+    def _trunk(self, bev, shape=None):
+        """bev: fp32 NCHW tensor, or (shape given) pixel fp16-pair rows [B*H*W, 2*C] with shape = (B, H, W, C)."""
+        first = None
+        if shape is None:
+            b, c, h, w = bev.shape
+            x = dc.nchw_to_pixel_h16(bev) if self.f16 else dc.nchw_to_pixel_split(bev)
+            shape = (b, h, w, c)
+        else:
+            if not self.f16 or self._first_zc is None:
+                raise ValueError("pixel fp16-pair input needs the f16 head")
+            x = bev
+            b = shape[0]
+            first = self._first_zc  # channels arrive in (z, c) order
         feats = []
-        for blk in self.blocks:
-            for conv in blk:
+        for bi, blk in enumerate(self.blocks):
+            for ci, conv in enumerate(blk):
+                if bi == 0 and ci == 0 and first is not None:
+                    conv = first
                 x, _, (b_, oh, ow) = conv(x, shape)
                 shape = (b_, oh, ow, conv.cout)
             feats.append((x, shape))
@@ -250,10 +277,14 @@ class DenseRPNHead:
         self._batched = None
         return self
 
-    def forward(self, bev):
+    def forward_h16(self, rows, shape):
+        """Same as forward() for a BEV given as pixel fp16-pair rows (SparseResNet3D.forward(pixel_h16=True))."""
+        return self.forward(rows, shape)
+
+    def forward(self, bev, shape=None):
         """bev [B, C, H, W] fp32 -> dict name -> list (per task) of [B, k, H, W] fp32 tensors.  The 36 ConvModules run as
-        one 64 -> 2304 convolution, the 36 output convs as one grouped CUDA-core launch."""
-        s, shape = self._trunk(bev)
+        one 64 -> 2304 convolution, the 36 output convs as one grouped launch."""
+        s, shape = self._trunk(bev, shape)
         bp = self._batched_params(bev.device)
         big = bp["big"]
         mid, _, _ = big(s, shape)  # [B*H*W] pixel rows of 36 * 64 channels

@@ -160,12 +160,13 @@ class SparseResNet3D:
         out += self.extra_conv[:2]
         return out
 
-    def init_weight(self, seed=0, device="cuda", randomize_bn=False):
-        """Seeded stand-in for SparseResNet3D.init_weight (sparse_resnet.py:177-183); no checkpoints exist offline."""
+    def init_weight(self, seed=0, device="cuda", randomize_bn=False, bn_gain=1.0):
+        """Seeded stand-in for SparseResNet3D.init_weight (sparse_resnet.py:177-183); no checkpoints exist offline.
+        bn_gain: see BatchNorm.init_parameters (sqrt(6) keeps activations O(1) through the 21 layers)."""
         rng = np.random.default_rng(seed)
         for l in self.all_layers():
             if isinstance(l, sp.BatchNorm):
-                l.init_parameters(rng, device, randomize=randomize_bn)
+                l.init_parameters(rng, device, randomize=randomize_bn, gain=bn_gain)
             else:
                 l.init_parameters(rng, device)
         return self
@@ -215,12 +216,14 @@ class SparseResNet3D:
         for dev, side in self._side.items():
             torch.cuda.current_stream(dev).wait_stream(side)
 
-    def forward(self, voxel_features, coors, batch_size, num=None):
+    def forward(self, voxel_features, coors, batch_size, num=None, pixel_h16=False):
+        """pixel_h16=False: the reference's dense BEV tensor [N, C*D, H, W] fp32.  True: the same tensor as pixel
+        fp16-pair rows (rows, (N, H, W, C*D)) for DenseRPNHead.forward_h16 - no fp32 NCHW pass in between."""
         out, feats = self.forward_sparse(voxel_features, coors, batch_size, num)
         # device counters [n_out, overflow, ...] of the 4 strided index sets: overflow != 0 means output sites were
         # dropped (capacity from set_level_caps too small) and the BEV tensor is incomplete; callers surface it
         self.level_counters = [t.index.counters for t in feats[1:]] + [out.index.counters]
-        dense = out.to_dense_bev()  # to_dense + transpose(0,4,1,2,3) + reshape [N, C*D, H, W]
+        dense = out.to_pixel_h16() if pixel_h16 else out.to_dense_bev()  # to_dense + transpose(0,4,1,2,3) + reshape
         self.join()
         return dense
 

@@ -86,6 +86,11 @@ def dense_conv2d(x_split, shape, packed, cout, n_tile, kernel, stride=1, padding
 # fp16-pair ("H16") path (csrc/dense_conv_f16.cu): the default of DenseRPNHead.  Images are pixel H16 rows
 # [B*H*W, 2*C] float16 = per pixel, groups of 32 channels [hi 32 | lo' 32]; x = hi + lo' * 2^-11.
 def n_tile_for_f16(cout):
+    """Output-channel tile.  P3D_DENSE_NTILE (tuning hook) forces 64 or 128 for the wide layers."""
+    import os
+    forced = os.environ.get("P3D_DENSE_NTILE")
+    if forced and cout >= 128:
+        return int(forced)
     return 128 if cout >= 128 else 64
 
 

@@ -177,6 +177,19 @@ class SparseCooTensor:
         return _ps.sparse_to_dense_bev(self.values(), self.index.coords, self.index.batch, self.index.spatial,
                                        num=self.index.num)
 
+    def to_pixel_h16(self):
+        """fp16-pair form of to_dense + transpose + reshape (sparse_resnet.py:202-206): pixel H16 rows
+        [batch * ny * nx, 2 * D * C] float16 (channel = z * C + c) for the fp16-pair dense RPN - the rows of the last layer
+        are scattered straight into it, no fp32 NCHW tensor is materialised."""
+        rows = self.get(ROWS_H16)
+        D, H, W = self.index.spatial
+        B = self.index.batch
+        out = torch.empty((B * H * W, 2 * D * self.channels), dtype=torch.float16, device=rows.device)
+        check(lib().p3d_sparse_rows_to_pixel_h16(ptr(rows), ptr(self.index.coords), ptr(self.index.num), self.index.cap,
+                                                 self.channels, B, D, H, W, ptr(out), stream(rows.device)),
+              "sparse_rows_to_pixel_h16")
+        return out, (B, H, W, D * self.channels)
+
 
 def sparse_coo_tensor(indices, values, shape, stop_gradient=True, num=None):
     """indices [4, nnz] (paddle layout) or [nnz, 4]; values [nnz, C]; shape [B, D, H, W, C]."""
@@ -268,6 +281,17 @@ def _run(p, t, want):
                                                          int(p.relu), ptr(out_f32), ptr(out_split), ptr(ws), wsb,
                                                          stream(dev)), "sparse_conv_gather_gemm_split_ws")
         t._vals[ROWS_F32], t._vals[ROWS_SPLIT] = out_f32, out_split
+    elif (p.precision == FP32 and want == ROWS_H16 and p.residual is None and p.cin <= 8 and p.cout in (16, 32)
+          and p.K * p.cin * p.cout * 4 <= 40 * 1024):
+        # the few-channel input layer feeding fp16-pair layers: exact fp32 FMAs, pair rows written by the same kernel
+        xin = p.x.get(ROWS_F32)
+        out_h16 = torch.empty((p.cap, 2 * p.cout), dtype=torch.float16, device=dev)
+        if PROFILE is not None:
+            s_ev.record(st)
+        check(L.p3d_sparse_conv_small_cin_h16(ptr(xin), ptr(p.nbr), ptr(p.num), p.cap, p.K, p.cin, p.cout, ptr(p.weight),
+                                              ptr(p.scale), ptr(p.shift), int(p.relu), None, ptr(out_h16),
+                                              ptr(status_tensor(dev)), stream(dev)), "sparse_conv_small_cin_h16")
+        t._vals[ROWS_H16] = out_h16
     else:
         xin = p.x.get(ROWS_F32)
         res = p.residual.get(ROWS_F32) if p.residual is not None else None
@@ -455,13 +479,17 @@ class BatchNorm(_Layer):
         self._folded = None
         self._bias_fold = {}  # conv bias tensor id -> folded shift (computed once, not per forward)
 
-    def init_parameters(self, rng, device, randomize=False):
+    def init_parameters(self, rng, device, randomize=False, gain=1.0):
+        """gain: multiplies gamma.  The reference's fresh initialisation (gamma 1 after uniform(+-1/sqrt(fan_in)) weights)
+        shrinks the activations by ~6x per conv + ReLU; sqrt(6) keeps them O(1) through the stack, which is the regime a
+        trained network runs in and the one in which an end-to-end parity check says something."""
         c = self.num_features
         if randomize:  # non-trivial statistics for tests
             g, b = rng.uniform(0.5, 1.5, c), rng.uniform(-0.2, 0.2, c)
             m, v = rng.uniform(-0.1, 0.1, c), rng.uniform(0.5, 1.5, c)
         else:  # constant_init(weight, 1), constant_init(bias, 0), running stats (0, 1): sparse_resnet.py:177-183
             g, b, m, v = np.ones(c), np.zeros(c), np.zeros(c), np.ones(c)
+        g = g * gain
         return self.set_parameters(*[torch.from_numpy(np.asarray(a, np.float32)).to(device) for a in (g, b, m, v)])
 
     def set_parameters(self, weight, bias, mean, variance):

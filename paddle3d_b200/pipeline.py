@@ -20,9 +20,29 @@ from .ops import sparse_nn as sp
 from .ops import voxelize as vox
 
 
+def _count_graph_nodes(raw_graph):
+    """Node counts of a cudaGraph_t by type, through libcudart (ctypes)."""
+    import ctypes as C
+    rt = C.CDLL("libcudart.so")
+    n = C.c_size_t(0)
+    g = C.c_void_p(int(raw_graph))
+    if rt.cudaGraphGetNodes(g, None, C.byref(n)) != 0:
+        return None
+    nodes = (C.c_void_p * n.value)()
+    if rt.cudaGraphGetNodes(g, nodes, C.byref(n)) != 0:
+        return None
+    names = {0: "kernel", 1: "memcpy", 2: "memset"}  # cudaGraphNodeType
+    out = {"kernel": 0, "memcpy": 0, "memset": 0, "other": 0}
+    for i in range(n.value):
+        t = C.c_int(0)
+        rt.cudaGraphNodeGetType(C.c_void_p(nodes[i]), C.byref(t))
+        out[names.get(t.value, "other")] += 1
+    return out
+
+
 class CenterPointHotPath:
     def __init__(self, cfg=None, device="cuda:0", precision=sp.FP32, seed=0, num_points=None, level_caps=None,
-                 head_seed=0, with_head=False):
+                 head_seed=0, with_head=False, keep_bev=True, bn_gain=1.0):
         self.cfg = dict(cfg or synth.C3)
         self.device = torch.device(device)
         self.n = int(num_points or self.cfg["num_points"])
@@ -30,7 +50,7 @@ class CenterPointHotPath:
         self.test_cfg = dict(synth.CENTERPOINT_TEST_CFG)
         self.label_off = synth.label_offsets()
         self.net = SparseResNet3D(self.F, self.cfg["voxel_size"], self.cfg["point_cloud_range"])
-        self.net.init_weight(seed=seed, device=self.device).set_precision(precision)
+        self.net.init_weight(seed=seed, device=self.device, bn_gain=bn_gain).set_precision(precision)
         V = self.cfg["max_voxels"]
         self.net.set_level_caps(level_caps or [3 * V, 3 * V, 2 * V, V])
         h = synth.centerpoint_head_outputs(head_seed)
@@ -42,7 +62,10 @@ class CenterPointHotPath:
         self.dense = None
         if with_head:
             from .dense_head import DenseRPNHead
-            self.dense = DenseRPNHead(in_channels=128 * 2).init_weight(seed=seed + 1, device=self.device)
+            self.dense = DenseRPNHead(in_channels=128 * 2).init_weight(seed=seed + 1, device=self.device, bn_gain=bn_gain)
+        # keep_bev=False (with the fp16-pair dense head): the sparse rows go straight into the pixel fp16-pair image the RPN
+        # reads; the reference's fp32 NCHW BEV tensor is then not materialised in the frame (bev_nchw() rebuilds it on demand)
+        self.keep_bev = keep_bev or self.dense is None or not self.dense.f16
         self.points = torch.zeros((self.n, self.F), dtype=torch.float32, device=self.device)  # static input
         self.graph = None
         self.out = None
@@ -59,16 +82,38 @@ class CenterPointHotPath:
         cfg, tc = self.cfg, self.test_cfg
         mean, coors, npv, nv = vox.voxelize_mean(self.points, cfg["voxel_size"], cfg["point_cloud_range"],
                                                  cfg["max_points"], cfg["max_voxels"], 0)
-        bev = self.net(mean, coors, 1, num=nv)
+        bev, bev_h16 = None, None
+        if self.keep_bev:
+            bev = self.net(mean, coors, 1, num=nv)
+            h = self.dense(bev) if self.dense is not None else self.head
+        else:
+            bev_h16 = self.net(mean, coors, 1, num=nv, pixel_h16=True)
+            h = self.dense.forward_h16(*bev_h16)
         # frame status word: [fp16-range overflow of the pair-row kernels, overflow flag of each strided level]
         status = torch.stack([sp.status_tensor(self.device)[0]] + [c[1] for c in self.net.level_counters])
-        h = self.dense(bev) if self.dense is not None else self.head
         boxes, scores, labels, counts = cpp.centerpoint_postprocess_device(
             h["hm"], h["reg"], h["height"], h["dim"], h["vel"], h["rot"], cfg["voxel_size"][:2],
             cfg["point_cloud_range"], tc["post_center_limit_range"], self.label_off, tc["down_ratio"],
             tc["score_threshold"], tc["nms_iou_threshold"], tc["nms_pre_max_size"], tc["nms_post_max_size"], True)
-        return dict(bev=bev, boxes=boxes, scores=scores, labels=labels, counts=counts, num_voxels=nv, coors=coors,
-                    mean=mean, status=status)
+        return dict(bev=bev, bev_h16=bev_h16, boxes=boxes, scores=scores, labels=labels, counts=counts, num_voxels=nv,
+                    coors=coors, mean=mean, status=status)
+
+    def bev_nchw(self):
+        """The dense BEV tensor [1, 256, H, W] fp32 of the last frame (rebuilt from the pixel fp16-pair image when the
+        frame did not materialise it)."""
+        if self.out["bev"] is not None:
+            self.stream.synchronize()
+            return self.out["bev"]
+        from .ops import dense_conv as dc
+        rows, shape = self.out["bev_h16"]
+        with torch.cuda.stream(self.stream):
+            out = dc.pixel_h16_to_nchw(rows, shape)
+            # pixel rows hold (z, c)-ordered channels (to_pixel_h16); the reference tensor is (c, z)-ordered
+            b, h, w, cd = shape
+            D = self.dense.bev_depth
+            out = out.view(b, D, cd // D, h, w).transpose(1, 2).reshape(b, cd, h, w).contiguous()
+        self.stream.synchronize()  # callers read it from other streams
+        return out
 
     def calibrate_head(self, points_dev):
         """Shift the heat-map biases of the (randomly initialised) dense head so that ~1.4 % of the BEV cells of this frame
@@ -86,23 +131,23 @@ class CenterPointHotPath:
         self.stream.synchronize()
         return self
 
-    def capture(self, warmup=2, dump_path=None):
-        """Warm up (sizes the workspaces) on the side stream, then capture the frame into a CUDA graph.  dump_path: also
-        write the graph's DOT description there (cudaGraphDebugDotPrint) so callers can count its nodes."""
+    def capture(self, warmup=2, count_nodes=False):
+        """Warm up (sizes the workspaces) on the side stream, then capture the frame into a CUDA graph.  count_nodes:
+        keep the cudaGraph_t and store its node counts (cudaGraphGetNodes / cudaGraphNodeGetType) in self.graph_nodes =
+        {"kernel": .., "memset": .., "memcpy": .., "other": ..}."""
         with torch.cuda.stream(self.stream):
             for _ in range(warmup):
                 self.out = self.forward_device()
             self.stream.synchronize()
-            self.graph = torch.cuda.CUDAGraph()
-            if dump_path is not None:
-                self.graph.enable_debug_mode()
+            self.graph = torch.cuda.CUDAGraph(keep_graph=True) if count_nodes else torch.cuda.CUDAGraph()
             with torch.cuda.graph(self.graph, stream=self.stream):
                 self.out = self.forward_device()
-            if dump_path is not None:
+            self.graph_nodes = None
+            if count_nodes:
                 try:
-                    self.graph.debug_dump(dump_path)
+                    self.graph_nodes = _count_graph_nodes(self.graph.raw_cuda_graph())
                 except Exception:  # noqa: BLE001  (a debugging aid must not take the pipeline down)
-                    pass
+                    self.graph_nodes = None
         self.stream.synchronize()
         return self
 

@@ -118,3 +118,30 @@ def test_deploy_predictor_matches_pipeline(cuda, tmp_path):
     out = tmp_path / "det.txt"
     deploy.write_results(str(out), b, l, s)
     assert len(out.read_text().splitlines()) == int((s >= 0).sum())
+
+
+def test_fused_pixel_h16_bev_matches_nchw_path(cuda):
+    """keep_bev=False (the bench frame): sparse rows -> pixel fp16-pair image -> dense head, no fp32 NCHW BEV in between.
+    The rebuilt BEV tensor equals the NCHW one to the pair format's 2^-22, the detections agree."""
+    import torch
+    pts = torch.from_numpy(_frames(1)[0]).pin_memory()
+    a = _pipe(cuda, 4, with_head=True, keep_bev=True)
+    b = _pipe(cuda, 4, with_head=True, keep_bev=False)
+    ra = a.infer(pts)
+    rb = b.infer(pts)
+    bev_a, bev_b = a.bev_nchw().cpu().numpy(), b.bev_nchw().cpu().numpy()
+    assert b.out["bev"] is None and bev_a.shape == bev_b.shape
+    np.testing.assert_allclose(bev_b, bev_a, rtol=2.0 ** -20, atol=1e-9)  # pair format: 2^-22 relative, 2^-36 absolute floor
+    # the dense head reads the pixel rows in (z, c) channel order through the permuted image of its first conv
+    ha, hb = a.dense(a.bev_nchw()), b.dense.forward_h16(*b.out["bev_h16"])
+    torch.cuda.synchronize()
+    for name in ha:
+        for x, y in zip(ha[name], hb[name]):
+            assert np.abs(x.cpu().numpy() - y.cpu().numpy()).max() <= 1e-5 * max(1.0, float(x.abs().max())), name
+    assert len(ra[2]) == len(rb[2])
+    same = (ra[2].numpy() == rb[2].numpy()).mean()
+    assert same > 0.98  # candidates within 1e-6 of each other may swap ranks
+    b.points.copy_(pts.to(cuda))
+    b.capture()
+    rc = b.infer(pts)
+    assert torch.equal(rc[0], rb[0]) and torch.equal(rc[2], rb[2])
