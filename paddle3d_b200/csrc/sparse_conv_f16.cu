@@ -878,7 +878,10 @@ extern "C" int p3d_sparse_conv_f16(const void *in_h16, const int32_t *nbr, const
   // tuning hooks: producer warps per CTA (P3D_F16_NPW = 4 / 8 / 16, default 8) and sub-tiles per pipeline stage
   // (P3D_F16_NSUB = 1 / 2; default: 2 for Cin <= 32 - 4 resp. 2 taps per stage -, 1 above; Cout = 128 always 1).
   // Measured on the C3 frame (profiles/r02_f16_sweep.md): 8 warps beat 4 by 5 % and 16 (register spills) by 14 %.
-  static const int npw = getenv("P3D_F16_NPW") ? atoi(getenv("P3D_F16_NPW")) : 8;
+  static const int npw_env = getenv("P3D_F16_NPW") ? atoi(getenv("P3D_F16_NPW")) : 0;
+  // 16 producer warps for the 16-channel layers (64-byte row gathers are the most LSU-bound: 41 vs 45 us per level-0
+  // layer, profiles/r02_f16_sweep.md), 8 elsewhere
+  const int npw = npw_env ? npw_env : (Cin == 16 ? 16 : 8);
   static const int nsub_env = getenv("P3D_F16_NSUB") ? atoi(getenv("P3D_F16_NSUB")) : 0;
   const int nsub = nsub_env ? nsub_env : (Cin <= 32 ? 2 : 1);
 #define P3D_F16_NPW(CI, CO, NS)                                        \

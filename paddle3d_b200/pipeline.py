@@ -189,6 +189,23 @@ class CenterPointHotPath:
                                    "output sites were dropped" % (lvl + 1))
 
     # ---- public end-to-end call for a sweep of frames: same per-frame work, copies overlapped with compute
+    def prepare_sweep(self):
+        """Copy stream, staging buffers, pinned result slots and events of infer_many (allocated once; pinned allocations
+        cost milliseconds, so callers that time a sweep call this first)."""
+        if getattr(self, "_copy_stream", None) is not None:
+            return self
+        self._copy_stream = torch.cuda.Stream(self.device)
+        self._staging = [torch.empty_like(self.points) for _ in range(2)]
+        self._slots = [dict(boxes=torch.empty_like(self.h_boxes).pin_memory(),
+                            scores=torch.empty_like(self.h_scores).pin_memory(),
+                            labels=torch.empty_like(self.h_labels).pin_memory(),
+                            counts=torch.empty_like(self.h_counts).pin_memory(),
+                            status=torch.zeros_like(self.h_status).pin_memory()) for _ in range(2)]
+        self._staged = [torch.cuda.Event() for _ in range(2)]    # H2D into staging[k] done
+        self._consumed = [torch.cuda.Event() for _ in range(2)]  # staging[k] copied into the graph's input
+        self._done = [torch.cuda.Event() for _ in range(2)]      # results of slot k are on the host
+        return self
+
     def infer_many(self, frames_host):
         """frames_host: iterable of pinned [n, F] fp32 tensors.  Yields (boxes, scores, labels) per frame, in order.
 
@@ -197,17 +214,7 @@ class CenterPointHotPath:
         results of frame i after it has submitted frame i+1."""
         if self.graph is None:
             raise RuntimeError("infer_many needs a captured pipeline: call capture() first")
-        if getattr(self, "_copy_stream", None) is None:
-            self._copy_stream = torch.cuda.Stream(self.device)
-            self._staging = [torch.empty_like(self.points) for _ in range(2)]
-            self._slots = [dict(boxes=torch.empty_like(self.h_boxes).pin_memory(),
-                                scores=torch.empty_like(self.h_scores).pin_memory(),
-                                labels=torch.empty_like(self.h_labels).pin_memory(),
-                                counts=torch.empty_like(self.h_counts).pin_memory(),
-                                status=torch.zeros_like(self.h_status).pin_memory()) for _ in range(2)]
-            self._staged = [torch.cuda.Event() for _ in range(2)]    # H2D into staging[k] done
-            self._consumed = [torch.cuda.Event() for _ in range(2)]  # staging[k] copied into the graph's input
-            self._done = [torch.cuda.Event() for _ in range(2)]      # results of slot k are on the host
+        self.prepare_sweep()
         cs, st = self._copy_stream, self.stream
 
         def result(k):

@@ -50,6 +50,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--iters", type=int, default=30)
     ap.add_argument("--only", default="")
+    ap.add_argument("--c3-only", action="store_true", help="voxelize: skip the KITTI config (for an ncu capture of the C3 launches)")
     args = ap.parse_args()
     only = set(x for x in args.only.split(",") if x)
     dev = torch.device("cuda:0")
@@ -70,6 +71,8 @@ def main():
 
     # hard_voxelize (whole op, 5 launches) — C2 and C3
     for cfg, gen in ((synth.C2, synth.lidar_cloud), (synth.C3, synth.lidar_cloud)):
+        if args.c3_only and cfg is synth.C2:
+            continue
         pts = torch.from_numpy(gen(cfg, 0)).to(dev)
         N, F, P, V = pts.shape[0], pts.shape[1], cfg["max_points"], cfg["max_voxels"]
         nbytes = 4 * N * F + 4 * V * P * F + 12 * V + 4 * V + 4
