@@ -1,7 +1,8 @@
-"""dense 2-D convolutions of the RPN / neck / CenterHead on tcgen05
-(`csrc/dense_conv_tc.cu`).  Images travel as "pixel split rows" [B*H*W, 2*C] fp32 (hi half of all channels, then lo
-half) between layers; weights are given in Paddle's layouts (Conv2D [Cout, Cin, kH, kW], Conv2DTranspose
-[Cin, Cout, k, k]).  Parity-green on a B200 (tests/test_gpu_dense.py); performance not measured yet."""
+"""dense 2-D convolutions of the RPN / neck / CenterHead on tcgen05.  Default: the fp16-pair kernels of
+`csrc/dense_conv_f16.cu` (second half of this file; per-layer timings in profiles/r02_dense_bench*.jsonl).  The first
+half drives the round-1 tf32-pair kernels (`csrc/dense_conv_tc.cu`, images as "pixel split rows" [B*H*W, 2*C] fp32), kept
+for models whose activations leave fp16's range.  Weights are given in Paddle's layouts (Conv2D [Cout, Cin, kH, kW],
+Conv2DTranspose [Cin, Cout, k, k])."""
 import torch
 
 from .._lib import check, lib
