@@ -182,6 +182,15 @@ int p3d_sparse_rulebook_conv_t(const int32_t *coords, const int32_t *n_in_dev, i
                                int32_t *n_out_dev, int64_t out_cap, void *table_out, size_t table_out_bytes,
                                int32_t *nbr, p3d_stream_t stream);
 
+/* One resolution level in two launches: p3d_sparse_rulebook_conv_t plus, when nbr_subm is given, the SubM neighbour map
+ * [out_cap, prod(subm_ksize)] of the NEW level (odd kernel, "same" padding) looked up in table_out - what a following
+ * p3d_sparse_rulebook_subm_t on the output index set would return. */
+int p3d_sparse_rulebook_level_t(const int32_t *coords, const int32_t *n_in_dev, int64_t n_in_cap, int batch,
+                                const int *spatial_host, const int *ksize_host, const int *stride_host,
+                                const int *pad_host, const void *table_in, size_t table_in_bytes, int32_t *out_coords,
+                                int32_t *n_out_dev, int64_t out_cap, void *table_out, size_t table_out_bytes,
+                                int32_t *nbr, const int *subm_ksize_host, int32_t *nbr_subm, p3d_stream_t stream);
+
 /* Unfused elementwise epilogue (BatchNorm(eval) / sparse.add / ReLU on a materialised tensor):
  *   out[r, c] = act(x[r, c] * scale[c] + shift[c] (+ residual[r, c])); out may alias x. */
 int p3d_sparse_affine_act(const float *x, const int32_t *n_dev, int64_t n_cap, int C, const float *scale,
@@ -343,6 +352,14 @@ int p3d_bev_pool_prepare(const float *coor, int B, int N, int D, int H, int W, c
 int p3d_grouped_head_conv_f16(const void *in_h16, int B, int H, int W, int in_C, int Cin, int groups,
                               const void *packed_weight, const float *bias, const int32_t *plane0_dev,
                               const int32_t *cnt_dev, int planes, float *out_nchw, int32_t *status_dev, p3d_stream_t stream);
+/* The same output convs with the 9 taps in the GEMM's N dimension (default for Cin = 32 / 64 / 128 and <= 3 output
+ * channels per group; a wider conv is split into several groups over the same input slice): one [256 haloed pixels x Cin]
+ * x [Cin x 27] GEMM per 14 x 14 output tile, then every pixel adds its 9 shifted partial sums.  Group g reads input
+ * channels [cin0[g], cin0[g] + Cin) (cin0_dev null: g * Cin); packed_weight: per group
+ * p3d_dense_conv2d_f16_pack_weights(taps 1, Cin, n_tile 32) of W2[c][tap * 3 + co]; bias [groups][4]. */
+int p3d_head_out_conv_f16(const void *in_h16, int B, int H, int W, int in_C, int Cin, int groups, const void *packed_weight,
+                          const float *bias, const int32_t *cin0_dev, const int32_t *plane0_dev, const int32_t *cnt_dev,
+                          int planes, float *out_nchw, p3d_stream_t stream);
 int p3d_dense_conv2d_f16(const void *in_h16, int B, int H, int W, int Cin, const void *packed_weight, int Cout, int n_tile,
                          int kh, int kw, int stride, int pad, int up, const float *scale, const float *shift, int relu,
                          void *out_h16, int out_C, int out_c0, float *out_nchw, int mode, int m_tiles,

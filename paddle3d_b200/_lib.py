@@ -47,6 +47,8 @@ SIGNATURES = {
     "p3d_sparse_rulebook_subm_t": (_int, [_vp, _vp, _i64, _int, _vp, _vp, _vp, _sz, _vp, _vp]),
     "p3d_sparse_rulebook_conv_t": (_int, [_vp, _vp, _i64, _int, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _vp, _i64, _vp, _sz,
                                           _vp, _vp]),
+    "p3d_sparse_rulebook_level_t": (_int, [_vp, _vp, _i64, _int, _vp, _vp, _vp, _vp, _vp, _sz, _vp, _vp, _i64, _vp, _sz,
+                                           _vp, _vp, _vp, _vp]),
     "p3d_sparse_affine_act": (_int, [_vp, _vp, _i64, _int, _vp, _vp, _vp, _int, _vp, _vp]),
     "p3d_sparse_conv_packed_weight_bytes": (_sz, [_int, _int, _int]),
     "p3d_sparse_conv_pack_weights": (_int, [_vp, _int, _int, _int, _vp, _vp]),
@@ -78,6 +80,7 @@ SIGNATURES = {
     "p3d_bev_pool_prepare_workspace_bytes": (_sz, [_i64]),
     "p3d_bev_pool_prepare": (_int, [_vp, _int, _int, _int, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _sz,
                                     _vp]),
+    "p3d_head_out_conv_f16": (_int, [_vp, _int, _int, _int, _int, _int, _int, _vp, _vp, _vp, _vp, _vp, _int, _vp, _vp]),
     "p3d_grouped_head_conv_f16": (_int, [_vp, _int, _int, _int, _int, _int, _int, _vp, _vp, _vp, _vp, _int, _vp, _vp, _vp]),
     "p3d_dense_conv2d_f16": (_int, [_vp, _int, _int, _int, _int, _vp, _int, _int, _int, _int, _int, _int, _int, _vp, _vp,
                                     _int, _vp, _int, _int, _vp, _int, _int, _vp, _vp]),

@@ -124,7 +124,8 @@ __global__ void __launch_bounds__(256) rb_neighbors_kernel(const int32_t *__rest
   }
 }
 
-// Strided conv: enumerate output sites.  Thread (i, k): candidate o = (in + pad - k) / stride.
+// Strided conv: enumerate output sites.  Thread (i, k): candidate o = (in + pad - k) / stride.  The warp's winners (first
+// claim of a site) are numbered with ONE atomicAdd per warp iteration.
 __global__ void __launch_bounds__(256) rb_outputs_kernel(const int32_t *__restrict__ coords,
                                                          const int32_t *__restrict__ n_dev, long long n_cap, Dims d,
                                                          unsigned long long *__restrict__ tab_out, uint32_t mask,
@@ -133,42 +134,110 @@ __global__ void __launch_bounds__(256) rb_outputs_kernel(const int32_t *__restri
   const int K = d.kd * d.kh * d.kw;
   const long long n = n_dev ? min(static_cast<long long>(n_dev[0]), n_cap) : n_cap;
   const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
-  for (long long q = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; q < n * K; q += stride) {
-    const int i = static_cast<int>(q / K), k = static_cast<int>(q - static_cast<long long>(i) * K);
-    const int4 c = *reinterpret_cast<const int4 *>(coords + static_cast<size_t>(i) * 4);
-    const int kz = k / (d.kh * d.kw), ky = (k / d.kw) % d.kh, kx = k % d.kw;
-    int oz = c.y + d.pd - kz, oy = c.z + d.ph - ky, ox = c.w + d.pw - kx;
-    if (oz < 0 || oy < 0 || ox < 0 || oz % d.sd || oy % d.sh || ox % d.sw) continue;
-    oz /= d.sd;
-    oy /= d.sh;
-    ox /= d.sw;
-    if (oz >= d.oD || oy >= d.oH || ox >= d.oW) continue;
-    const uint32_t key = lin(c.x, oz, oy, ox, d.oD, d.oH, d.oW);
-    uint32_t h = hash32(key) >> shift;
-    for (uint32_t probes = 0;; ++probes) {
-      if (probes > mask) {  // table full (far more sites than out_cap): cannot dedupe any more, flag overflow
-        n_out_dev[3] = 1;
-        break;
+  const int lane = threadIdx.x & 31;
+  // warp-uniform trip count (q0 = the warp's first query): the ballot below needs all 32 lanes
+  for (long long q0 = static_cast<long long>(blockIdx.x) * blockDim.x + (threadIdx.x & ~31); q0 < n * K; q0 += stride) {
+    const long long q = q0 + lane;
+    bool won = false;
+    uint32_t h = 0, key = 0;
+    int4 oc = make_int4(0, 0, 0, 0);
+    if (q < n * K) {
+      const int i = static_cast<int>(q / K), k = static_cast<int>(q - static_cast<long long>(i) * K);
+      const int4 c = *reinterpret_cast<const int4 *>(coords + static_cast<size_t>(i) * 4);
+      const int kz = k / (d.kh * d.kw), ky = (k / d.kw) % d.kh, kx = k % d.kw;
+      int oz = c.y + d.pd - kz, oy = c.z + d.ph - ky, ox = c.w + d.pw - kx;
+      bool cand = !(oz < 0 || oy < 0 || ox < 0 || oz % d.sd || oy % d.sh || ox % d.sw);
+      if (cand) {
+        oz /= d.sd;
+        oy /= d.sh;
+        ox /= d.sw;
+        cand = oz < d.oD && oy < d.oH && ox < d.oW;
       }
-      unsigned long long cur = tab_out[h];
-      if (cur == kEmpty) {
-        // claim the slot; the winner numbers the site
-        const unsigned long long want = (static_cast<unsigned long long>(key) << 32) | 0xfffffffeu;
-        cur = atomicCAS(&tab_out[h], kEmpty, want);
-        if (cur == kEmpty) {
-          const int id = atomicAdd(&n_out_dev[2], 1);  // raw counter; the clamped copy is published by rb_finish
-          if (id < out_cap) {
-            int4 oc = make_int4(c.x, oz, oy, ox);
-            *reinterpret_cast<int4 *>(out_coords + static_cast<size_t>(id) * 4) = oc;
-            // publish the row id: this table doubles as the coordinate table of the OUTPUT index set (same key, one
-            // aligned 8-byte store; concurrent probes only compare the key half)
-            tab_out[h] = (static_cast<unsigned long long>(key) << 32) | static_cast<uint32_t>(id);
+      if (cand) {
+        key = lin(c.x, oz, oy, ox, d.oD, d.oH, d.oW);
+        oc = make_int4(c.x, oz, oy, ox);
+        h = hash32(key) >> shift;
+        for (uint32_t probes = 0;; ++probes) {
+          if (probes > mask) {  // table full (far more sites than out_cap): cannot dedupe any more, flag overflow
+            n_out_dev[3] = 1;
+            break;
           }
-          break;
+          unsigned long long cur = tab_out[h];
+          if (cur == kEmpty) {
+            // claim the slot; the winner numbers the site below
+            const unsigned long long want = (static_cast<unsigned long long>(key) << 32) | 0xfffffffeu;
+            cur = atomicCAS(&tab_out[h], kEmpty, want);
+            if (cur == kEmpty) {
+              won = true;
+              break;
+            }
+          }
+          if (static_cast<uint32_t>(cur >> 32) == key) break;
+          h = (h + 1) & mask;
         }
       }
-      if (static_cast<uint32_t>(cur >> 32) == key) break;
-      h = (h + 1) & mask;
+    }
+    const unsigned int winners = __ballot_sync(0xffffffffu, won);
+    if (winners) {
+      int base = 0;
+      if (lane == __ffs(winners) - 1) base = atomicAdd(&n_out_dev[2], __popc(winners));  // raw counter (clamped copy: [0])
+      base = __shfl_sync(0xffffffffu, base, __ffs(winners) - 1);
+      if (won) {
+        const int id = base + __popc(winners & ((1u << lane) - 1u));
+        if (id < out_cap) {
+          *reinterpret_cast<int4 *>(out_coords + static_cast<size_t>(id) * 4) = oc;
+          // publish the row id: this table doubles as the coordinate table of the OUTPUT index set (same key, one
+          // aligned 8-byte store; concurrent probes only compare the key half)
+          tab_out[h] = (static_cast<unsigned long long>(key) << 32) | static_cast<uint32_t>(id);
+        }
+      }
+    }
+  }
+}
+
+// One launch per resolution level after rb_outputs: publishes the clamped output count / overflow flag (what
+// rb_finish_kernel did) and fills BOTH neighbour maps of the new index set: the strided conv's (rows of the input level,
+// through tab_in) and, when nbr_m is given, the 3-D SubM map of the level's residual blocks (rows of the output level,
+// through tab_out, which rb_outputs completed).  Query q < n * Ks: strided; else SubM.
+__global__ void __launch_bounds__(256) rb_level_neighbors_kernel(const int32_t *__restrict__ out_coords,
+                                                                 int32_t *__restrict__ n_out_dev, long long out_cap, Dims ds,
+                                                                 const unsigned long long *__restrict__ tab_in,
+                                                                 uint32_t mask_in, uint32_t shift_in, int32_t *__restrict__ nbr_s,
+                                                                 Dims dm, const unsigned long long *__restrict__ tab_out,
+                                                                 uint32_t mask_out, uint32_t shift_out,
+                                                                 int32_t *__restrict__ nbr_m) {
+  const int raw = n_out_dev[2];
+  const long long n = raw < out_cap ? raw : out_cap;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    n_out_dev[0] = static_cast<int32_t>(n);
+    n_out_dev[1] = (raw > out_cap || n_out_dev[3]) ? 1 : 0;
+  }
+  const int Ks = ds.kd * ds.kh * ds.kw, Km = nbr_m ? dm.kd * dm.kh * dm.kw : 0;
+  const long long total = n * (Ks + Km), split = n * Ks;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long q = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x; q < total; q += stride) {
+    if (q < split) {
+      const int o = static_cast<int>(q / Ks), k = static_cast<int>(q - static_cast<long long>(o) * Ks);
+      const int4 c = *reinterpret_cast<const int4 *>(out_coords + static_cast<size_t>(o) * 4);
+      const int kz = k / (ds.kh * ds.kw), ky = (k / ds.kw) % ds.kh, kx = k % ds.kw;
+      const int iz = c.y * ds.sd - ds.pd + kz, iy = c.z * ds.sh - ds.ph + ky, ix = c.w * ds.sw - ds.pw + kx;
+      int r = -1;
+      if (iz >= 0 && iz < ds.D && iy >= 0 && iy < ds.H && ix >= 0 && ix < ds.W)
+        r = lookup(tab_in, mask_in, shift_in, lin(c.x, iz, iy, ix, ds.D, ds.H, ds.W));
+      nbr_s[q] = r;
+    } else {
+      const long long qm = q - split;
+      const int o = static_cast<int>(qm / Km), k = static_cast<int>(qm - static_cast<long long>(o) * Km);
+      const int4 c = *reinterpret_cast<const int4 *>(out_coords + static_cast<size_t>(o) * 4);
+      const int kz = k / (dm.kh * dm.kw), ky = (k / dm.kw) % dm.kh, kx = k % dm.kw;
+      const int iz = c.y - dm.pd + kz, iy = c.z - dm.ph + ky, ix = c.w - dm.pw + kx;
+      int r = -1;
+      if (kz == dm.kd / 2 && ky == dm.kh / 2 && kx == dm.kw / 2) {
+        r = o;
+      } else if (iz >= 0 && iz < dm.D && iy >= 0 && iy < dm.H && ix >= 0 && ix < dm.W) {
+        r = lookup(tab_out, mask_out, shift_out, lin(c.x, iz, iy, ix, dm.D, dm.H, dm.W));
+      }
+      nbr_m[qm] = r;
     }
   }
 }
@@ -621,24 +690,33 @@ extern "C" int p3d_sparse_rulebook_subm_t(const int32_t *coords, const int32_t *
   return P3D_OK;
 }
 
-extern "C" int p3d_sparse_rulebook_conv_t(const int32_t *coords, const int32_t *n_in_dev, int64_t n_in_cap, int batch,
-                                          const int *spatial_host, const int *ksize_host, const int *stride_host,
-                                          const int *pad_host, const void *table_in, size_t table_in_bytes,
-                                          int32_t *out_coords, int32_t *n_out_dev, int64_t out_cap, void *table_out,
-                                          size_t table_out_bytes, int32_t *nbr, p3d_stream_t stream) {
+// One resolution level: output sites + table of the strided conv, its neighbour map and (optionally) the SubM map of the
+// new level's blocks (kernel subm_ksize_host, odd sizes, "same" padding) in two launches.
+extern "C" int p3d_sparse_rulebook_level_t(const int32_t *coords, const int32_t *n_in_dev, int64_t n_in_cap, int batch,
+                                           const int *spatial_host, const int *ksize_host, const int *stride_host,
+                                           const int *pad_host, const void *table_in, size_t table_in_bytes,
+                                           int32_t *out_coords, int32_t *n_out_dev, int64_t out_cap, void *table_out,
+                                           size_t table_out_bytes, int32_t *nbr, const int *subm_ksize_host,
+                                           int32_t *nbr_subm, p3d_stream_t stream) {
   Dims d;
   int rc = make_dims(batch, spatial_host, ksize_host, stride_host, pad_host, 0, &d);
   if (rc) return rc;
   Tab ti, to;
   if (n_in_cap < 0 || out_cap < 1 || n_in_cap > 0x7fffffff / 128 || out_cap > 0x7fffffff / 128 || !n_out_dev ||
       !out_coords || !nbr || (n_in_cap && !coords) || !tab_of(const_cast<void *>(table_in), table_in_bytes, n_in_cap, &ti) ||
-      !tab_of(table_out, table_out_bytes, out_cap, &to))
+      !tab_of(table_out, table_out_bytes, out_cap, &to) || (nbr_subm && !subm_ksize_host))
     return P3D_ERR_INVALID_ARG;
   if ((reinterpret_cast<uintptr_t>(coords) & 15) || (reinterpret_cast<uintptr_t>(out_coords) & 15))
     return P3D_ERR_INVALID_ARG;
   if (static_cast<long long>(batch) * d.oD * d.oH * d.oW >= 0xffffffffll) return P3D_ERR_UNSUPPORTED;
+  Dims dm = d;
+  if (nbr_subm) {
+    const int osp[3] = {d.oD, d.oH, d.oW};
+    rc = make_dims(batch, osp, subm_ksize_host, nullptr, nullptr, 1, &dm);
+    if (rc) return rc;
+  }
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int K = d.kd * d.kh * d.kw;
+  const int K = d.kd * d.kh * d.kw, Km = nbr_subm ? dm.kd * dm.kh * dm.kw : 0;
   P3D_CUDA_CHECK(cudaMemsetAsync(to.p, 0xff, static_cast<size_t>(to.cap) * 8, st));
   P3D_CUDA_CHECK(cudaMemsetAsync(n_out_dev, 0, sizeof(int32_t) * 4, st));
   if (n_in_cap > 0) {
@@ -647,10 +725,18 @@ extern "C" int p3d_sparse_rulebook_conv_t(const int32_t *coords, const int32_t *
                                                                     static_cast<int>(out_cap));
     P3D_LAUNCH_CHECK();
   }
-  rb_finish_kernel<<<1, 1, 0, st>>>(n_out_dev, static_cast<int>(out_cap));
-  P3D_LAUNCH_CHECK();
-  rb_neighbors_kernel<<<persistent_grid(out_cap * K), 256, 0, st>>>(out_coords, n_out_dev, out_cap, d, ti.p, ti.cap - 1,
-                                                                   ti.shift, 0, nbr);
+  rb_level_neighbors_kernel<<<persistent_grid(out_cap * (K + Km)), 256, 0, st>>>(
+      out_coords, n_out_dev, out_cap, d, ti.p, ti.cap - 1, ti.shift, nbr, dm, to.p, to.cap - 1, to.shift, nbr_subm);
   P3D_LAUNCH_CHECK();
   return P3D_OK;
+}
+
+extern "C" int p3d_sparse_rulebook_conv_t(const int32_t *coords, const int32_t *n_in_dev, int64_t n_in_cap, int batch,
+                                          const int *spatial_host, const int *ksize_host, const int *stride_host,
+                                          const int *pad_host, const void *table_in, size_t table_in_bytes,
+                                          int32_t *out_coords, int32_t *n_out_dev, int64_t out_cap, void *table_out,
+                                          size_t table_out_bytes, int32_t *nbr, p3d_stream_t stream) {
+  return p3d_sparse_rulebook_level_t(coords, n_in_dev, n_in_cap, batch, spatial_host, ksize_host, stride_host, pad_host,
+                                     table_in, table_in_bytes, out_coords, n_out_dev, out_cap, table_out, table_out_bytes,
+                                     nbr, nullptr, nullptr, stream);
 }

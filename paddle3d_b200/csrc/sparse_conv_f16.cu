@@ -146,6 +146,71 @@ __device__ __forceinline__ uint32_t split_taps(int split, int splits, int K) {
   return m;
 }
 
+// Work decomposition of one launch.  stream = 0: items (tile, split), split s owns the taps t == s (mod splits), item
+// w = blockIdx.x + it * gridDim.x.  stream = 1 ("stream-K"): the n_tiles * K (tile, tap) units are cut into g_eff equal
+// contiguous ranges, one per CTA; a CTA's items are the tiles its range touches, each with the contiguous tap range that
+// falls inside.  A tile cut by range boundaries has `pieces` partial sums (its CTAs are consecutive: piece = CTA - first
+// CTA), combined through the slabs / ticket like the splits.  No wave quantisation: 309 tiles on 148 CTAs cost 56 taps
+// per CTA instead of 3 x 27.  Ranges are never shorter than ceil((K - 1) / (kMaxSplits - 1)) units, so pieces <= kMaxSplits.
+struct Sched {
+  int stream, splits, K;
+  long long n_work;          // stream = 0: n_tiles * splits
+  long long total, g_eff;    // stream = 1
+  long long u0, u1;          // stream = 1: this CTA's unit range
+};
+__device__ __forceinline__ Sched make_sched(long long n_tiles, int K, int smax, int mode, int fix_taps) {
+  Sched sc;
+  sc.K = K;
+  sc.stream = 0;
+  const int grid = static_cast<int>(gridDim.x);
+  sc.splits = choose_splits(n_tiles, grid, K, smax);
+  sc.n_work = n_tiles * sc.splits;
+  sc.total = n_tiles * K;
+  sc.g_eff = 1;
+  sc.u0 = sc.u1 = 0;
+  if (mode && smax >= 4 && sc.total > 0) {  // slabs for 4 pieces available
+    const int u_min = (K - 1 + 2) / 3 > 1 ? (K - 1 + 2) / 3 : 1;  // ceil((K - 1) / (kMaxSplits - 1)), kMaxSplits = 4
+    long long g = sc.total / u_min;
+    if (g > grid) g = grid;
+    if (g < 1) g = 1;
+    const long long waves = (sc.n_work + grid - 1) / grid;
+    const long long cost_old = waves * ((K + sc.splits - 1) / sc.splits + 4 + (sc.splits > 1 ? 1 : 0));
+    const long long cost_stream = (sc.total + g - 1) / g + 4 + fix_taps;
+    if (mode == 2 || cost_stream < cost_old) {
+      sc.stream = 1;
+      sc.g_eff = g;
+      const long long c = blockIdx.x;
+      if (c < g) {
+        sc.u0 = c * sc.total / g;
+        sc.u1 = (c + 1) * sc.total / g;
+      }
+    }
+  }
+  return sc;
+}
+// item `it` of this CTA: false when the CTA has no more items
+__device__ __forceinline__ bool sched_item(const Sched &sc, int it, long long &tile, uint32_t &mask, int &piece, int &pieces) {
+  if (!sc.stream) {
+    const long long w = static_cast<long long>(blockIdx.x) + static_cast<long long>(it) * gridDim.x;
+    if (w >= sc.n_work) return false;
+    tile = w / sc.splits;
+    piece = static_cast<int>(w - tile * sc.splits);
+    pieces = sc.splits;
+    mask = split_taps(piece, pieces, sc.K);
+    return true;
+  }
+  tile = sc.u0 / sc.K + it;
+  const long long start = tile * sc.K;
+  if (start >= sc.u1) return false;
+  const int ta = static_cast<int>((sc.u0 > start ? sc.u0 : start) - start);
+  const int tb = static_cast<int>((sc.u1 < start + sc.K ? sc.u1 : start + sc.K) - start);
+  mask = (tb >= 32 ? 0xffffffffu : ((1u << tb) - 1u)) & ~((1u << ta) - 1u);
+  const long long cf = ((start + 1) * sc.g_eff - 1) / sc.total, cl = ((start + sc.K) * sc.g_eff - 1) / sc.total;
+  piece = static_cast<int>(static_cast<long long>(blockIdx.x) - cf);
+  pieces = static_cast<int>(cl - cf + 1);
+  return true;
+}
+
 struct Params {
   const uint8_t *in;        // H16 rows [n_in][4 * CIN bytes]
   const int32_t *nbr;       // [n_cap][K]
@@ -165,6 +230,7 @@ struct Params {
   const uint8_t *zero_row;  // 512 zero bytes in global memory (target of missing neighbours with flag 2)
   long long *dbg;           // debug only (p3d_debug_f16_timeline): clock64 timeline of CTA `dbg_cta`, layout below
   int dbg_cta;
+  int sk_mode, sk_fix;      // stream-K: 0 off, 1 when the cost model prefers it, 2 always; cost of a fix-up in taps
   int flags;                // tuning / debug: 1 all neighbours missing, 2 missing neighbours read zero_row instead of a
                             // zero-size copy, 4 all neighbours present (pseudo-random rows); 1 and 4 give wrong results
 };
@@ -186,9 +252,8 @@ __global__ void __launch_bounds__((NPW + 7) * 32, 1) conv_f16_kernel(const Param
   const long long n = p.n_out_dev ? min(static_cast<long long>(p.n_out_dev[0]), p.n_cap) : p.n_cap;
   const long long n_tiles = (n + kM - 1) / kM;
   const int K = p.K;
-  const int splits = choose_splits(n_tiles, static_cast<int>(gridDim.x), K, p.smax);
-  const long long n_work = n_tiles * splits;
-  if (static_cast<long long>(blockIdx.x) >= n_work) return;
+  const Sched sc = make_sched(n_tiles, K, p.smax, p.sk_mode, p.sk_fix);
+  if (sc.stream ? (sc.u0 >= sc.u1) : (static_cast<long long>(blockIdx.x) >= sc.n_work)) return;
 
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -209,8 +274,8 @@ __global__ void __launch_bounds__((NPW + 7) * 32, 1) conv_f16_kernel(const Param
   const bool dbgl = dbgc && lane == 0;
   if (dbgc && tid == 0) {
     p.dbg[8192] = clock64();
-    p.dbg[8195] = n_work;
-    p.dbg[8196] = splits;
+    p.dbg[8195] = sc.stream ? (sc.u1 - sc.u0) : sc.n_work;
+    p.dbg[8196] = sc.stream ? -sc.g_eff : sc.splits;
   }
   if (tid == kMmaWarp * 32) {
     for (int s = 0; s < S; ++s) {
@@ -254,12 +319,12 @@ __global__ void __launch_bounds__((NPW + 7) * 32, 1) conv_f16_kernel(const Param
     int it = 0;
     int cuse = 0;
     const bool dp = dbgl && wid == 0;
-    for (long long w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
+    long long tile;
+    uint32_t m;
+    int piece, pieces;
+    for (; sched_item(sc, it, tile, m, piece, pieces); ++it) {
       const int b = it & 1;
-      const long long tile = w / splits;
-      const int split = static_cast<int>(w - tile * splits);
       const int rows = static_cast<int>(min(static_cast<long long>(kM), n - tile * kM));
-      uint32_t m = split_taps(split, splits, K);
       const int n_taps = __popc(m);
       const int n_sub = (CIN == 16) ? (n_taps + 1) / 2 : n_taps * C::G;
       mbar_wait(smem_u32(&s_bar[kNY + b]), static_cast<uint32_t>((it >> 1) & 1));
@@ -369,10 +434,11 @@ __global__ void __launch_bounds__((NPW + 7) * 32, 1) conv_f16_kernel(const Param
     const size_t tiles_cap = static_cast<size_t>((p.n_cap + kM - 1) / kM);
     bool ovf = false;
     int it = 0;
-    for (long long w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
+    long long tile;
+    uint32_t item_mask;
+    int split, splits;  // piece of the tile this item computes / number of pieces the tile is cut into
+    for (; sched_item(sc, it, tile, item_mask, split, splits); ++it) {
       const int b = it & 1;
-      const long long tile = w / splits;
-      const int split = static_cast<int>(w - tile * splits);
       const long long row0 = tile * kM;
       const int rows = static_cast<int>(min(static_cast<long long>(kM), n - row0));
       const bool live = r < rows;
@@ -531,11 +597,12 @@ __global__ void __launch_bounds__((NPW + 7) * 32, 1) conv_f16_kernel(const Param
     uint32_t fph = 0;  // parity to wait for on full[s]
     int it = 0;
     int cuse = 0;
-    for (long long w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
+    long long tile;
+    uint32_t item_mask;
+    int piece, pieces;
+    for (; sched_item(sc, it, tile, item_mask, piece, pieces); ++it) {
       const int b = it & 1;
-      const long long tile = w / splits;
-      const int split = static_cast<int>(w - tile * splits);
-      const int n_taps = __popc(split_taps(split, splits, K));
+      const int n_taps = __popc(item_mask);
       const int n_sub = (CIN == 16) ? (n_taps + 1) / 2 : n_taps * C::G;
       mbar_wait(smem_u32(&s_bar[kTE + b]), static_cast<uint32_t>(((it >> 1) & 1) ^ 1));  // epilogue of item it - 2 done
       tc_fence_after();
@@ -581,10 +648,10 @@ __global__ void __launch_bounds__((NPW + 7) * 32, 1) conv_f16_kernel(const Param
       int s = 0;
       uint32_t eph = 1;
       int cuse = 0;
-      for (long long w = blockIdx.x; w < n_work; w += gridDim.x) {
-        const long long tile = w / splits;
-        const int split = static_cast<int>(w - tile * splits);
-        uint32_t m = split_taps(split, splits, K);
+      long long tile;
+      uint32_t m;
+      int piece, pieces;
+      for (int it = 0; sched_item(sc, it, tile, m, piece, pieces); ++it) {
         const int n_taps = __popc(m);
         const int n_sub = (CIN == 16) ? (n_taps + 1) / 2 : n_taps * C::G;
         int k = 0;
@@ -645,9 +712,11 @@ __global__ void __launch_bounds__((NPW + 7) * 32, 1) conv_f16_kernel(const Param
   } else {
     // ------------------------------------------------------------------------------------------ neighbour-map prefetch
     int it = 0;
-    for (long long w = blockIdx.x; w < n_work; w += gridDim.x, ++it) {
+    long long tile;
+    uint32_t item_mask;
+    int piece, pieces;
+    for (; sched_item(sc, it, tile, item_mask, piece, pieces); ++it) {
       const int b = it & 1;
-      const long long tile = w / splits;
       const long long row0 = tile * kM;
       int32_t *nb = s_nbr + b * nbr_words;
       mbar_wait(smem_u32(&s_bar[kNE + b]), static_cast<uint32_t>(((it >> 1) & 1) ^ 1));  // buffer free (item it - 2 done)
@@ -791,7 +860,7 @@ extern "C" int p3d_sparse_conv_f16_pack_weights(const float *weight, int K, int 
 // dense layers (csrc/dense_conv_f16.cu): the same k-block image for one N tile, W[tap][Cin][n_tile], any Cin % 32 == 0
 extern "C" int p3d_dense_conv2d_f16_pack_weights(const float *weight_tci, int taps, int Cin, int n_tile, void *packed,
                                                  int32_t *status_dev, p3d_stream_t stream) {
-  if (!weight_tci || !packed || taps < 1 || Cin < 32 || Cin % 32 || (n_tile != 16 && n_tile != 64 && n_tile != 128))
+  if (!weight_tci || !packed || taps < 1 || Cin < 32 || Cin % 32 || (n_tile != 16 && n_tile != 32 && n_tile != 64 && n_tile != 128))
     return P3D_ERR_INVALID_ARG;
   const long long total = static_cast<long long>(taps) * Cin * n_tile;
   f16::pack_weights_kernel<<<div_up(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
@@ -872,6 +941,12 @@ extern "C" int p3d_sparse_conv_f16(const void *in_h16, const int32_t *nbr, const
     if (static_cast<size_t>(smax) > fit) smax = static_cast<int>(fit);
   }
   p.smax = smax < 1 ? 1 : smax;
+  // stream-K (contiguous (tile, tap) ranges per CTA instead of whole tiles) when the device-side cost model prefers it:
+  // P3D_F16_STREAMK = 0 off / 1 auto (default) / 2 always; P3D_F16_SKFIX = cost of a tile's fix-up in taps (default 6)
+  static const int sk_env = getenv("P3D_F16_STREAMK") ? atoi(getenv("P3D_F16_STREAMK")) : 1;
+  static const int skfix_env = getenv("P3D_F16_SKFIX") ? atoi(getenv("P3D_F16_SKFIX")) : 6;
+  p.sk_mode = sk_env;
+  p.sk_fix = skfix_env;
   p.counters = p.smax > 1 ? static_cast<int32_t *>(workspace) : nullptr;
   p.slabs = p.smax > 1 ? reinterpret_cast<float *>(static_cast<char *>(workspace) + tick) : nullptr;
   cudaStream_t st = static_cast<cudaStream_t>(stream);

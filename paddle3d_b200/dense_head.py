@@ -7,6 +7,8 @@ pair operands on tcgen05 (csrc/dense_conv_f16.cu, `f16=True`); the round-1 tf32-
 (`f16=False`) for data outside fp16's range.  The 36 ConvModules of the heads run as ONE 64 -> 2304 convolution and
 the 36 output convs as one grouped CUDA-core launch (forward); forward_per_head keeps the layer-by-layer form for
 the parity tests."""
+import os
+
 import numpy as np
 import torch
 
@@ -22,7 +24,7 @@ class _Conv:
         self.cin, self.cout, self.k, self.stride, self.padding, self.up = cin, cout, k, stride, padding, up
         self.has_bias, self.bn_eps, self.relu = bias, bn_eps, relu
         self.f16 = f16 and cout >= 16  # the 1-3 channel output convs of the heads run on the CUDA cores (forward)
-        self.n_tile = dc.n_tile_for_f16(cout) if self.f16 else dc.n_tile_for(cout)
+        self.n_tile = dc.n_tile_for_f16(cout, cin, k, stride, padding, up) if self.f16 else dc.n_tile_for(cout)
         self.np = None
         self.dev = None
 
@@ -190,7 +192,11 @@ class DenseRPNHead:
         b, H, W, cin = shape
         gp = groups_params
         planes = torch.empty((b, planes_total, H, W), dtype=torch.float32, device=device)
-        if self.f16:
+        if self.f16 and "packed9" in gp and not os.environ.get("P3D_HEAD_OUT_N16"):
+            check(lib().p3d_head_out_conv_f16(ptr(mid), b, H, W, in_C, cin, int(gp["cnt9"].numel()), ptr(gp["packed9"]),
+                                              ptr(gp["bias9"]), ptr(gp["cin0_9"]), ptr(gp["plane0_9"]), ptr(gp["cnt9"]),
+                                              planes_total, ptr(planes), stream(device)), "head_out_conv_f16")
+        elif self.f16:
             check(lib().p3d_grouped_head_conv_f16(ptr(mid), b, H, W, in_C, cin, len(gp["cnt"]), ptr(gp["packed16"]),
                                                   ptr(gp["bias16"]), ptr(gp["plane0_dev"]), ptr(gp["cnt_dev"]), planes_total,
                                                   ptr(planes), ptr(dc._status(device)), stream(device)), "grouped_head_conv_f16")
@@ -232,6 +238,33 @@ class DenseRPNHead:
                                                           ptr(dc._status(device)), stream(device)), "pack_weights")
             out.update(packed16=packed, bias16=torch.from_numpy(b16).to(device),
                        plane0_dev=torch.from_numpy(out["plane0"]).to(device), cnt_dev=torch.from_numpy(out["cnt"]).to(device))
+            if cin in (32, 64, 128):
+                # tap-as-N form (p3d_head_out_conv_f16): W2[c][tap * 3 + j]; a conv with more than 3 output channels
+                # becomes several virtual groups over the same input slice
+                w9, b9, cin0, pl0, cn = [], [], [], [], []
+                for g, (_, f) in enumerate(finals):
+                    for j0 in range(0, f.cout, 3):
+                        k = min(3, f.cout - j0)
+                        w27 = np.zeros((cin, 9, 3), np.float32)
+                        w27[:, :, :k] = w16[g][:, :, j0:j0 + k].transpose(1, 0, 2)  # [tap][c][j] -> [c][tap][j]
+                        w2 = np.zeros((cin, 32), np.float32)
+                        w2[:, :27] = w27.reshape(cin, 27)
+                        bb = np.zeros((4,), np.float32)
+                        bb[:k] = b16[g, j0:j0 + k]
+                        w9.append(w2)
+                        b9.append(bb)
+                        cin0.append(g * cin)
+                        pl0.append(int(plane0[g]) + j0)
+                        cn.append(k)
+                blk9 = cin * 32 * 4
+                packed9 = torch.zeros((len(w9) * blk9,), dtype=torch.uint8, device=device)
+                for v, w2 in enumerate(w9):
+                    wt = torch.from_numpy(w2).to(device)
+                    check(L.p3d_dense_conv2d_f16_pack_weights(ptr(wt), 1, cin, 32, ptr(packed9[v * blk9:(v + 1) * blk9]),
+                                                              ptr(dc._status(device)), stream(device)), "pack_weights")
+                i32 = lambda a: torch.from_numpy(np.asarray(a, np.int32)).to(device)  # noqa: E731
+                out.update(packed9=packed9, bias9=torch.from_numpy(np.stack(b9)).to(device), cin0_9=i32(cin0),
+                           plane0_9=i32(pl0), cnt9=i32(cn))
         else:
             out.update(fw=torch.from_numpy(fw).to(device), fb=torch.from_numpy(fb).to(device))
         return out

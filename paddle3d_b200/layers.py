@@ -141,6 +141,7 @@ class SparseResNet3D:
         for cout, k, s, p, key in self.STAGES:
             down = [sp.Conv3D(cin, cout, k, s, padding=p, bias_attr=False), sp.BatchNorm(cout, epsilon=1e-3, momentum=0.01),
                     sp.ReLU()]
+            down[0].fuse_subm = ((3, 3, 3), key)  # the level's SubM map comes out of the strided conv's rulebook launch
             self.stages.append((down, [_BasicBlock(cout, key), _BasicBlock(cout, key)]))
             cin = cout
         self.extra_conv = [sp.Conv3D(128, 128, (3, 1, 1), (2, 1, 1), bias_attr=False),

@@ -418,14 +418,24 @@ class _ConvBase(_Layer):
         L = lib()
         tab_in = src.table()
         tab_out = torch.empty((L.p3d_sparse_table_bytes(cap),), dtype=torch.uint8, device=dev)
-        check(L.p3d_sparse_rulebook_conv_t(ptr(src.coords), ptr(src.num), src.cap, src.batch, host_ints(src.spatial),
-                                           host_ints(self.kernel_size), host_ints(self.stride),
-                                           host_ints(self.padding), ptr(tab_in), tab_in.numel(), ptr(out_coords),
-                                           ptr(n_out), cap, ptr(tab_out), tab_out.numel(), ptr(nbr), stream(dev)),
-              "sparse_rulebook_conv_t")
+        # fuse_subm = (ksize, key) of the SubM blocks that follow on the new level: their neighbour map comes out of the
+        # same launch (p3d_sparse_rulebook_level_t) instead of a separate p3d_sparse_rulebook_subm_t call
+        fuse = getattr(self, "fuse_subm", None)
+        nbr_subm = sub_ks = None
+        if fuse is not None:
+            sub_ks = tuple(int(v) for v in fuse[0])
+            nbr_subm = torch.empty((cap, sub_ks[0] * sub_ks[1] * sub_ks[2]), dtype=torch.int32, device=dev)
+        check(L.p3d_sparse_rulebook_level_t(ptr(src.coords), ptr(src.num), src.cap, src.batch, host_ints(src.spatial),
+                                            host_ints(self.kernel_size), host_ints(self.stride),
+                                            host_ints(self.padding), ptr(tab_in), tab_in.numel(), ptr(out_coords),
+                                            ptr(n_out), cap, ptr(tab_out), tab_out.numel(), ptr(nbr),
+                                            host_ints(sub_ks) if sub_ks else None, ptr(nbr_subm), stream(dev)),
+              "sparse_rulebook_level_t")
         osp = [(src.spatial[a] + 2 * self.padding[a] - self.kernel_size[a]) // self.stride[a] + 1 for a in range(3)]
         index = _IndexSet(out_coords, n_out, cap, src.batch, osp, table=tab_out)
         index.counters = n_out
+        if nbr_subm is not None:
+            index.subm_rulebooks[(fuse[1] if fuse[1] is not None else "_anon", sub_ks)] = nbr_subm
         src.strided[id(self)] = (index, nbr)
         return index, nbr
 

