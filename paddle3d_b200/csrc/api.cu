@@ -1,9 +1,15 @@
 // C-ABI housekeeping + precision dispatch for libp3d_b200.
 #include "common.cuh"
 
+#include <stdlib.h>
+
 namespace p3d {
 thread_local int g_last_cuda_error = 0;
+bool pdl_enabled() {
+  static const bool on = !(getenv("P3D_PDL") && atoi(getenv("P3D_PDL")) == 0);
+  return on;
 }
+}  // namespace p3d
 
 extern "C" int p3d_sparse_conv_gather_gemm_fp32(const float *in, const int32_t *nbr, const int32_t *n_out_dev,
                                                 int64_t n_out_cap, int K, int Cin, int Cout, const float *weight,

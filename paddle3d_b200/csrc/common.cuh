@@ -46,6 +46,27 @@ inline uint32_t next_pow2(uint64_t x) {
 
 constexpr int kNumSMs = 148;  // B200
 
+// Programmatic dependent launch: the grid may be scheduled while its predecessor in the stream drains.  Every kernel
+// launched this way executes pdl_wait() before it touches global memory (and pdl_trigger() first, so that ITS successor
+// can be scheduled early as well).  P3D_PDL=0 falls back to plain stream order.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 __device__ __forceinline__ uint32_t hash32(uint32_t k) {
   k *= 0x9E3779B1u;  // Fibonacci hashing; callers take the top bits
   return k;

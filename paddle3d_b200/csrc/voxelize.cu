@@ -31,9 +31,9 @@ namespace {
 
 constexpr unsigned long long kEmpty = ~0ull;
 constexpr int kInf = 0x7fffffff;
-constexpr int kScanBlock = 1024;
+constexpr int kScanBlock = 512;
 constexpr int kScanItems = 4;                       // consecutive points per thread of the rank scan
-constexpr int kScanTile = kScanBlock * kScanItems;  // points per block: 74 look-back hops at 300k points, not 293
+constexpr int kScanTile = kScanBlock * kScanItems;  // points per block: 147 blocks at 300k points (one per SM), <= 5 look-back rounds
 
 struct VoxGeom {
   float min_x, min_y, min_z;
@@ -71,6 +71,8 @@ VoxWs carve(void *ws, int64_t n, int P, int V) {
 // ---------------------------------------------------------------- K0
 __global__ void vox_init_kernel(uint4 *table16, size_t n_table16, uint4 *desc16, size_t n_desc16, uint4 *lists16,
                                 size_t n_lists16) {
+  pdl_trigger();
+  pdl_wait();
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
   const size_t tid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const uint4 ones = make_uint4(~0u, ~0u, ~0u, ~0u);
@@ -98,6 +100,8 @@ __device__ __forceinline__ int cell_of(const float *__restrict__ pt, const VoxGe
 __global__ void __launch_bounds__(256) vox_insert_kernel(const float *__restrict__ points, int n, int F, VoxGeom g,
                                                          unsigned long long *__restrict__ table, uint32_t mask,
                                                          uint32_t shift, int32_t *__restrict__ pt_slot) {
+  pdl_trigger();
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const unsigned active = __ballot_sync(0xffffffffu, i < n);
   if (i >= n) return;
@@ -137,6 +141,8 @@ __global__ void __launch_bounds__(kScanBlock) vox_rank_kernel(const unsigned lon
                                                               int32_t *__restrict__ coords, int coord_stride,
                                                               int coord_off, int batch_id,
                                                               int32_t *__restrict__ num_voxels) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ unsigned int s_bid;
   __shared__ int s_warp[kScanBlock / 32];
   __shared__ int s_prefix;
@@ -176,34 +182,42 @@ __global__ void __launch_bounds__(kScanBlock) vox_rank_kernel(const unsigned lon
   if (lane == 31) s_warp[wid] = inc;
   __syncthreads();
   if (wid == 0) {
-    const int v = s_warp[lane];
+    const int v = lane < kScanBlock / 32 ? s_warp[lane] : 0;
     int winc = v;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
       const int t = __shfl_up_sync(0xffffffffu, winc, d);
       if (lane >= d) winc += t;
     }
-    s_warp[lane] = winc - v;  // exclusive warp offsets
+    if (lane < kScanBlock / 32) s_warp[lane] = winc - v;  // exclusive warp offsets
     const int aggregate = __shfl_sync(0xffffffffu, winc, 31);
-    if (lane == 0) {
-      // decoupled look-back: status 1 = block aggregate, 2 = inclusive prefix
-      int prefix = 0;
-      volatile unsigned long long *vd = desc + 1;
-      if (bid == 0) {
-        vd[0] = (2ull << 32) | static_cast<uint32_t>(aggregate);
-      } else {
-        vd[bid] = (1ull << 32) | static_cast<uint32_t>(aggregate);
-        int j = static_cast<int>(bid) - 1;
-        while (true) {
-          unsigned long long d = vd[j];
-          const uint32_t st = static_cast<uint32_t>(d >> 32);
-          if (st == 0) continue;
-          prefix += static_cast<int>(static_cast<uint32_t>(d));
-          if (st == 2) break;
-          --j;
-        }
-        vd[bid] = (2ull << 32) | static_cast<uint32_t>(prefix + aggregate);
+    // decoupled look-back, 32 predecessors per round (status 1 = block aggregate, 2 = inclusive prefix)
+    int prefix = 0;
+    volatile unsigned long long *vd = desc + 1;
+    if (bid == 0) {
+      if (lane == 0) vd[0] = (2ull << 32) | static_cast<uint32_t>(aggregate);
+    } else {
+      if (lane == 0) vd[bid] = (1ull << 32) | static_cast<uint32_t>(aggregate);
+      int j = static_cast<int>(bid) - 1;  // lane l inspects block j - l
+      while (true) {
+        const int b = j - lane;
+        const unsigned long long d = b >= 0 ? vd[b] : (2ull << 32);  // before block 0: inclusive prefix 0
+        const uint32_t st = static_cast<uint32_t>(d >> 32);
+        const unsigned incl = __ballot_sync(0xffffffffu, st == 2);
+        const unsigned ready = __ballot_sync(0xffffffffu, st != 0);
+        const int last = incl ? __ffs(incl) - 1 : 31;                     // nearest inclusive prefix (or all 32)
+        const unsigned need = last == 31 ? 0xffffffffu : ((2u << last) - 1u);
+        if ((ready & need) != need) continue;                             // a needed predecessor has not posted yet
+        int val = lane <= last ? static_cast<int>(static_cast<uint32_t>(d)) : 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) val += __shfl_xor_sync(0xffffffffu, val, o);
+        prefix += val;
+        if (incl) break;
+        j -= 32;
       }
+      if (lane == 0) vd[bid] = (2ull << 32) | static_cast<uint32_t>(prefix + aggregate);
+    }
+    if (lane == 0) {
       s_prefix = prefix;
       if (bid == gridDim.x - 1) {
         const int total = prefix + aggregate;
@@ -236,6 +250,8 @@ __global__ void __launch_bounds__(kScanBlock) vox_rank_kernel(const unsigned lon
 __global__ void __launch_bounds__(256) vox_slots_kernel(const int32_t *__restrict__ pt_slot,
                                                         const int32_t *__restrict__ slot_vox, int n, int P,
                                                         int32_t *__restrict__ lists) {
+  pdl_trigger();
+  pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const int slot = pt_slot[i];
@@ -243,9 +259,27 @@ __global__ void __launch_bounds__(256) vox_slots_kernel(const int32_t *__restric
   const int v = slot_vox[slot];
   if (v < 0) return;
   int32_t *L = lists + static_cast<size_t>(v) * P;
+  // Every list entry only ever decreases.  So (a) once the LAST entry is below i, i can never be among the P smallest:
+  // one read retires almost every point of an over-full cell (the hot cells of a dense cloud used to serialise
+  // P atomics per point); (b) the levels whose entry is already below i can be skipped, and reading them all at
+  // once (independent loads, one L2 round trip) instead of one dependent read per level shortens the chain.
+  if (__ldcg(L + P - 1) < i) return;
+  int s = 0;
+  for (int s0 = 0; s0 < P; s0 += 8) {
+    int val[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) val[k] = (s0 + k < P) ? __ldcg(L + s0 + k) : kInf;
+    // lists are not guaranteed sorted mid-flight: only the LEADING run of "already smaller" levels may be skipped
+    int lead = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) lead += (lead == k && val[k] < i) ? 1 : 0;
+    s += lead;
+    if (lead < 8) break;
+  }
+  if (s >= P) return;
   int cur = i;
-  for (int s = 0; s < P; ++s) {
-    if (L[s] < cur) continue;  // resident is already smaller: it can only shrink further (monotone), skip the atomic
+  for (; s < P; ++s) {
+    if (__ldcg(L + s) < cur) continue;  // resident is already smaller: it can only shrink further (monotone), skip the atomic
     const int old = atomicMin(&L[s], cur);
     if (old == kInf) break;     // landed in a free slot
     if (old > cur) cur = old;   // displaced a larger index: carry it down
@@ -255,63 +289,44 @@ __global__ void __launch_bounds__(256) vox_slots_kernel(const int32_t *__restric
 // ---------------------------------------------------------------- K4
 __device__ __forceinline__ void st_stream(float4 *p, float4 v) { __stcs(p, v); }
 
-constexpr int kWriteUnroll = 4;  // float4 stores per thread: 4 independent lists -> points -> store chains in flight
+constexpr int kWriteRows = 256;  // (voxel, slot) rows per block of the writer
 
-__global__ void __launch_bounds__(256) vox_write_kernel(const float *__restrict__ points, int F, int P, int V,
-                                                        const int32_t *__restrict__ lists,
-                                                        const int32_t *__restrict__ num_voxels_dev,
-                                                        float *__restrict__ voxels, int32_t *__restrict__ coords,
-                                                        int32_t *__restrict__ npv, long long total4,
-                                                        long long total) {
-  const int PF = P * F;
-  const long long blk0 = static_cast<long long>(blockIdx.x) * (256 * kWriteUnroll);
-  float4 o[kWriteUnroll];
-#pragma unroll
-  for (int u = 0; u < kWriteUnroll; ++u) {
-    const long long q = blk0 + u * 256 + threadIdx.x;  // consecutive threads -> consecutive float4: coalesced
-    float r[4] = {0.f, 0.f, 0.f, 0.f};
-    if (q < total4) {
-      const long long e0 = q * 4;
-      int v = static_cast<int>(e0 / PF);
-      int rem = static_cast<int>(e0 - static_cast<long long>(v) * PF);
-      int s = rem / F;
-      int f = rem - s * F;
-      int idx = __ldg(lists + static_cast<size_t>(v) * P + s);
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        r[k] = (idx != kInf) ? __ldg(points + static_cast<size_t>(idx) * F + f) : 0.f;
-        if (++f == F) {
-          f = 0;
-          if (++s == P) {
-            s = 0;
-            ++v;
-          }
-          if (k < 3 && v < V) idx = __ldg(lists + static_cast<size_t>(v) * P + s);
-        }
-      }
-    }
-    o[u] = make_float4(r[0], r[1], r[2], r[3]);
-  }
-#pragma unroll
-  for (int u = 0; u < kWriteUnroll; ++u) {
-    const long long q = blk0 + u * 256 + threadIdx.x;
-    if (q < total4) st_stream(reinterpret_cast<float4 *>(voxels) + q, o[u]);
-  }
-  const long long gtid = static_cast<long long>(blockIdx.x) * 256 + threadIdx.x;
-  if (gtid == 0) {
-    // scalar tail when V*P*F is not a multiple of 4
-    for (long long e = total4 * 4; e < total; ++e) {
-      const int v = static_cast<int>(e / PF);
-      const int rem = static_cast<int>(e - static_cast<long long>(v) * PF);
-      const int idx = lists[static_cast<size_t>(v) * P + rem / F];
-      voxels[e] = (idx != kInf) ? points[static_cast<size_t>(idx) * F + rem % F] : 0.f;
+// One block = 256 consecutive (voxel, slot) rows of voxels[V, P, F]: each thread reads ITS row's point index (coalesced)
+// and copies the F floats of that point (or zeros) into shared memory; then the block streams the 256 * F floats out as
+// float4, fully coalesced - every byte of the output is written exactly once, no integer division on the store path.
+__global__ void __launch_bounds__(kWriteRows) vox_write_kernel(const float *__restrict__ points, int F, int P, int V,
+                                                               const int32_t *__restrict__ lists,
+                                                               const int32_t *__restrict__ num_voxels_dev,
+                                                               float *__restrict__ voxels, int32_t *__restrict__ coords,
+                                                               int32_t *__restrict__ npv, long long rows_total) {
+  extern __shared__ __align__(16) float s_stage[];  // [kWriteRows][F]
+  pdl_trigger();
+  pdl_wait();
+  const int tid = threadIdx.x;
+  const long long r0 = static_cast<long long>(blockIdx.x) * kWriteRows;
+  const int nrows = static_cast<int>(min(static_cast<long long>(kWriteRows), rows_total - r0));
+  if (tid < nrows) {
+    const int idx = __ldg(lists + r0 + tid);
+    float *dst = s_stage + tid * F;
+    if (idx != kInf) {
+      const float *src = points + static_cast<size_t>(idx) * F;
+      for (int f = 0; f < F; ++f) dst[f] = __ldg(src + f);
+    } else {
+      for (int f = 0; f < F; ++f) dst[f] = 0.f;
     }
   }
+  __syncthreads();
+  const int cnt = nrows > 0 ? nrows * F : 0;
+  float *out = voxels + r0 * F;  // r0 is a multiple of 256: 16-byte aligned whenever `voxels` is
+  const int c4 = cnt >> 2;
+  for (int q = tid; q < c4; q += kWriteRows) st_stream(reinterpret_cast<float4 *>(out) + q, reinterpret_cast<const float4 *>(s_stage)[q]);
+  for (int e = (c4 << 2) + tid; e < cnt; e += kWriteRows) out[e] = s_stage[e];
   // per-voxel outputs: one thread per voxel, strided over the grid
-  for (long long v = gtid; v < V; v += static_cast<long long>(gridDim.x) * 256) {
-    int cnt = 0;
-    for (int s = 0; s < P; ++s) cnt += (lists[static_cast<size_t>(v) * P + s] != kInf);
-    npv[v] = cnt;
+  const long long gtid = static_cast<long long>(blockIdx.x) * kWriteRows + tid;
+  for (long long v = gtid; v < V; v += static_cast<long long>(gridDim.x) * kWriteRows) {
+    int c = 0;
+    for (int s = 0; s < P; ++s) c += (__ldg(lists + static_cast<size_t>(v) * P + s) != kInf);
+    npv[v] = c;
     if (v >= num_voxels_dev[0]) {
       coords[v * 3 + 0] = 0;
       coords[v * 3 + 1] = 0;
@@ -326,6 +341,8 @@ __global__ void __launch_bounds__(256) vox_mean_kernel(const float *__restrict__
                                                        const int32_t *__restrict__ num_voxels_dev,
                                                        float *__restrict__ mean, int32_t *__restrict__ coors4,
                                                        int32_t *__restrict__ npv) {
+  pdl_trigger();
+  pdl_wait();
   const long long q = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
   if (q >= static_cast<long long>(V) * F) return;
   const int v = static_cast<int>(q / F), f = static_cast<int>(q - static_cast<long long>(v) * F);
@@ -387,18 +404,14 @@ int run_front(const float *points, int n, int F, const VoxGeom &g, int P, int V,
   const size_t n_t16 = static_cast<size_t>(w.cap) / 2;
   const size_t n_d16 = (static_cast<size_t>(w.nblocks) + 1 + 1) / 2;  // carve() pads to 256 B
   const size_t n_l16 = (static_cast<size_t>(V) * P + 3) / 4;
-  vox_init_kernel<<<kNumSMs * 4, 256, 0, st>>>(reinterpret_cast<uint4 *>(w.table), n_t16,
-                                               reinterpret_cast<uint4 *>(w.desc), n_d16,
-                                               reinterpret_cast<uint4 *>(w.lists), n_l16);
-  P3D_LAUNCH_CHECK();
+  P3D_CUDA_CHECK(launch_pdl(vox_init_kernel, dim3(kNumSMs * 4), dim3(256), 0, st, reinterpret_cast<uint4 *>(w.table), n_t16,
+                            reinterpret_cast<uint4 *>(w.desc), n_d16, reinterpret_cast<uint4 *>(w.lists), n_l16));
   if (n > 0) {
-    vox_insert_kernel<<<div_up(n, 256), 256, 0, st>>>(points, n, F, g, w.table, w.cap - 1, w.shift, w.pt_slot);
-    P3D_LAUNCH_CHECK();
-    vox_rank_kernel<<<w.nblocks, kScanBlock, 0, st>>>(w.table, w.pt_slot, n, V, g, w.desc, w.slot_vox, coords,
-                                                      coord_stride, coord_off, batch_id, num_voxels);
-    P3D_LAUNCH_CHECK();
-    vox_slots_kernel<<<div_up(n, 256), 256, 0, st>>>(w.pt_slot, w.slot_vox, n, P, w.lists);
-    P3D_LAUNCH_CHECK();
+    P3D_CUDA_CHECK(launch_pdl(vox_insert_kernel, dim3(div_up(n, 256)), dim3(256), 0, st, points, n, F, g, w.table,
+                              w.cap - 1, w.shift, w.pt_slot));
+    P3D_CUDA_CHECK(launch_pdl(vox_rank_kernel, dim3(w.nblocks), dim3(kScanBlock), 0, st, w.table, w.pt_slot, n, V, g, w.desc,
+                              w.slot_vox, coords, coord_stride, coord_off, batch_id, num_voxels));
+    P3D_CUDA_CHECK(launch_pdl(vox_slots_kernel, dim3(div_up(n, 256)), dim3(256), 0, st, w.pt_slot, w.slot_vox, n, P, w.lists));
   } else {
     P3D_CUDA_CHECK(cudaMemsetAsync(num_voxels, 0, sizeof(int32_t), st));
   }
@@ -433,14 +446,13 @@ extern "C" int p3d_hard_voxelize(const float *points, int64_t num_points, int nu
   const int n = static_cast<int>(num_points);
   rc = run_front(points, n, num_point_dim, g, max_points, max_voxels, w, coords, 3, 0, 0, num_voxels, st);
   if (rc) return rc;
-  const long long total = static_cast<long long>(max_voxels) * max_points * num_point_dim;
-  const long long total4 = total / 4;
-  const long long per_block = 256 * kWriteUnroll;
-  long long blocks = (total4 + per_block - 1) / per_block;
-  if (blocks < 1) blocks = 1;
-  vox_write_kernel<<<static_cast<unsigned int>(blocks), 256, 0, st>>>(points, num_point_dim, max_points, max_voxels, w.lists,
-                                                        num_voxels, voxels, coords, num_points_per_voxel, total4,
-                                                        total);
+  const long long rows_total = static_cast<long long>(max_voxels) * max_points;
+  const long long blocks = (rows_total + kWriteRows - 1) / kWriteRows;
+  const size_t stage = static_cast<size_t>(kWriteRows) * num_point_dim * sizeof(float);
+  if (stage > 48 * 1024) return P3D_ERR_UNSUPPORTED;  // F <= 48 point features
+  P3D_CUDA_CHECK(launch_pdl(vox_write_kernel, dim3(static_cast<unsigned int>(blocks)), dim3(kWriteRows), stage, st, points,
+                            num_point_dim, max_points, max_voxels, w.lists, num_voxels, voxels, coords,
+                            num_points_per_voxel, rows_total));
   P3D_LAUNCH_CHECK();
   return P3D_OK;
 }
@@ -464,9 +476,8 @@ extern "C" int p3d_voxelize_mean(const float *points, int64_t num_points, int nu
                  batch_id, num_voxels, st);
   if (rc) return rc;
   const long long threads = static_cast<long long>(max_voxels) * num_point_dim;
-  vox_mean_kernel<<<div_up(threads, 256), 256, 0, st>>>(points, num_point_dim, max_points, max_voxels, w.lists,
-                                                       num_voxels, mean, coors4, num_points_per_voxel);
-  P3D_LAUNCH_CHECK();
+  P3D_CUDA_CHECK(launch_pdl(vox_mean_kernel, dim3(div_up(threads, 256)), dim3(256), 0, st, points, num_point_dim, max_points,
+                            max_voxels, w.lists, num_voxels, mean, coors4, num_points_per_voxel));
   return P3D_OK;
 }
 

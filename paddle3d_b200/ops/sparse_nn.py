@@ -16,6 +16,7 @@ to_dense, .values()).  conv -> bn -> relu, and conv -> bn -> add -> relu, are on
 Row counts stay on the device (`num`), buffers are sized by capacity, no host sync anywhere.
 """
 import math
+import os
 
 import numpy as np
 import torch
@@ -35,6 +36,9 @@ FP32, TF32X3, TF32X3_SPLIT, TF32X3_TMA, F16X3 = 0, 1, 2, 3, 4
 ROWS_F32, ROWS_SPLIT, ROWS_H16 = 0, 1, 2  # activation layouts: [n, C] fp32 | [n][2][C] tf32 hi/lo | fp16 hi/lo' pairs
 _default_precision = [FP32]
 F16_MAX_SPLITS = 4
+# F16X3 layers with (Cin, Cout) in {(16,16), (16,32), (32,32)} run on the register-gather warp-MMA kernel
+# (csrc/sparse_conv_wm.cu: same rows, same arithmetic, missing neighbours are free); P3D_SPARSE_WM=0 keeps them on tcgen05
+NARROW_WM = [os.environ.get("P3D_SPARSE_WM", "1") != "0"]
 _status = {}
 
 
@@ -231,7 +235,7 @@ def prepare_rulebooks(index, conv_layers, side_stream):
 
 class _Pending:
     __slots__ = ("x", "nbr", "num", "cap", "K", "cin", "cout", "weight", "scale", "shift", "residual", "relu", "precision",
-                 "ready")
+                 "ready", "wm")
 
 
 PROFILE = None  # set to a list to record (cin, cout, K, precision, nbr, num, start_event, end_event) per conv launch
@@ -254,6 +258,15 @@ def _run(p, t, want):
         out_h16 = torch.empty((p.cap, 2 * p.cout), dtype=torch.float16, device=dev) if want == ROWS_H16 else None
         if PROFILE is not None:
             s_ev.record(st)
+        if p.wm:
+            check(L.p3d_sparse_conv_wm(ptr(xin), ptr(p.nbr), ptr(p.num), p.cap, p.K, p.cin, p.cout, ptr(p.weight),
+                                       ptr(p.scale), ptr(p.shift), ptr(res), int(p.relu), ptr(out_f32), ptr(out_h16),
+                                       ptr(status_tensor(dev)), stream(dev)), "sparse_conv_wm")
+            t._vals[ROWS_F32], t._vals[ROWS_H16] = out_f32, out_h16
+            if PROFILE is not None:
+                e_ev.record(st)
+                PROFILE.append((p.cin, p.cout, p.K, p.precision, p.nbr, p.num, s_ev, e_ev))
+            return
         wsb = L.p3d_sparse_conv_f16_workspace_bytes(p.cap, p.cout, F16_MAX_SPLITS)
         # one scratch buffer per (capacity, channels): its head holds the self-cleaning split-K tickets (zero on creation)
         ws = workspace(wsb, dev, "f16_splitk_%d_%d" % (p.cap, p.cout), zero=True) if wsb else None
@@ -377,14 +390,20 @@ class _ConvBase(_Layer):
             self.bias = torch.from_numpy(b).to(device)
         return self
 
-    def _packed_weight(self, K, f16=False):
-        """tf32 hi/lo (or fp16 hi/lo') shared-memory image of the weights, built once per layer."""
-        attr = "_packed_f16" if f16 else "_packed"
+    def _packed_weight(self, K, f16=False, wm=False):
+        """tf32 hi/lo (or fp16 hi/lo') shared-memory image of the weights, built once per layer (wm: the fragment-order
+        image of the warp-MMA kernel)."""
+        attr = "_packed_wm" if wm else "_packed_f16" if f16 else "_packed"
         pk = getattr(self, attr, None)
         if pk is None or pk[0] != self.weight.data_ptr():
             L = lib()
             dev = self.weight.device
-            if f16:
+            if wm:
+                nbytes = L.p3d_sparse_conv_wm_packed_weight_bytes(K, self.in_channels, self.out_channels)
+                buf = torch.empty((nbytes // 4,), dtype=torch.float32, device=dev)
+                check(L.p3d_sparse_conv_wm_pack_weights(ptr(self.weight), K, self.in_channels, self.out_channels, ptr(buf),
+                                                        ptr(status_tensor(dev)), stream(dev)), "sparse_conv_wm_pack_weights")
+            elif f16:
                 nbytes = L.p3d_sparse_conv_f16_packed_weight_bytes(K, self.in_channels, self.out_channels)
                 buf = torch.empty((nbytes // 4,), dtype=torch.float32, device=dev)
                 check(L.p3d_sparse_conv_f16_pack_weights(ptr(self.weight), K, self.in_channels, self.out_channels, ptr(buf),
@@ -447,10 +466,14 @@ class _ConvBase(_Layer):
         p.x, p.K, p.cin, p.cout = x, K, self.in_channels, self.out_channels
         p.weight, p.scale, p.shift, p.residual, p.relu = self.weight, None, self.bias, None, False
         p.ready = None
+        p.wm = False
         p.precision = self.precision if self.precision is not None else _default_precision[0]
         if p.precision == F16X3:
             if not lib().p3d_sparse_conv_f16_packed_weight_bytes(K, self.in_channels, self.out_channels):
                 p.precision = FP32  # e.g. the 5-channel input layer stays on the exact fp32 path
+            elif NARROW_WM[0] and lib().p3d_sparse_conv_wm_packed_weight_bytes(K, self.in_channels, self.out_channels):
+                p.wm = True
+                p.weight = self._packed_weight(K, wm=True)
             else:
                 p.weight = self._packed_weight(K, f16=True)
         elif p.precision in (TF32X3, TF32X3_SPLIT, TF32X3_TMA):

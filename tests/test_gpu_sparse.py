@@ -74,6 +74,63 @@ def test_single_conv(cuda, oracle_mod, precision, subm, ks, st, pd, cin, cout):
     rel_check('single_conv bev', bev, want_bev)
 
 
+@pytest.mark.parametrize("wm", [True, False])
+@pytest.mark.parametrize("subm,ks,st,pd,cin,cout,residual", [
+    (True, 3, 1, 1, 16, 16, True), (True, 3, 1, 1, 32, 32, True), (True, 3, 1, 1, 32, 32, False),
+    (False, 3, 2, 1, 16, 32, False), (True, (3, 1, 1), 1, (1, 0, 0), 16, 16, False),
+])
+def test_narrow_layers_on_both_kernels(cuda, oracle_mod, wm, subm, ks, st, pd, cin, cout, residual):
+    """The 16/32-channel layers of the fp16-pair path: register-gather warp-MMA kernel (csrc/sparse_conv_wm.cu, default)
+    and the tcgen05 kernel (P3D_SPARSE_WM=0) against the oracle - conv + BN (+ residual) + ReLU, fp32 and H16 outputs,
+    a row count that is not a multiple of 16."""
+    import torch
+    from paddle3d_b200.ops import sparse_nn as sp
+    rng = np.random.default_rng(cin * 17 + cout + (5 if residual else 0))
+    B, D, H, W = 2, 9, 33, 41
+    coords = _rand_sites(rng, B, D, H, W, 0.11)
+    if len(coords) % 16 == 0:
+        coords = coords[:-3]
+    feats = rng.normal(size=(len(coords), cin)).astype(np.float32)
+    cls = sp.SubmConv3D if subm else sp.Conv3D
+    conv = cls(cin, cout, ks, st, padding=pd, bias_attr=True).init_parameters(rng, cuda)
+    conv.precision = sp.F16X3
+    bn = sp.BatchNorm(cout, epsilon=1e-3).init_parameters(rng, cuda, randomize=True)
+    x = sp.sparse_coo_tensor(_t(cuda, coords).t(), _t(cuda, feats), [B, D, H, W, cin])
+    old = sp.NARROW_WM[0]
+    sp.NARROW_WM[0] = wm
+    def lazy():
+        y = bn(conv(x))
+        assert y._pending.wm == wm
+        if residual:
+            y = sp.add(y, x)
+        return sp.ReLU()(y)
+
+    try:
+        y = lazy()
+        vals = y.values()                      # the kernel writes fp32 rows
+        vals16 = lazy().get(sp.ROWS_H16)       # the kernel writes the pair rows itself
+    finally:
+        sp.NARROW_WM[0] = old
+    n = y.nnz()
+    w = conv.weight.cpu().numpy()
+    oc, of, osp, _ = oracle_mod.sparse_conv3d(coords, feats, B, (D, H, W), w, conv.stride, conv.padding, subm)
+    of = oracle_mod.bn_relu(of + conv.bias.cpu().numpy(), bn.weight.cpu().numpy(), bn.bias.cpu().numpy(),
+                            bn._mean.cpu().numpy(), bn._variance.cpu().numpy(), 1e-3, relu=True,
+                            residual=feats if residual else None)
+    assert n == len(oc)
+    want = _dense(oc, of, B, osp)
+    got = _dense(y.index.coords.cpu().numpy()[:n], vals.cpu().numpy()[:n], B, y.index.spatial)
+    rel_check('narrow %s wm=%d %d->%d' % ('subm' if subm else 'conv', wm, cin, cout), got, want)
+    if vals16 is not None:  # the pair rows the next layer would consume, converted back by the library
+        back = torch.empty((y.index.cap, cout), dtype=torch.float32, device=cuda)
+        from paddle3d_b200._lib import check, lib
+        from paddle3d_b200._mem import ptr, stream
+        check(lib().p3d_rows_convert_h16(ptr(vals16), 0, ptr(y.index.num), y.index.cap, cout, ptr(back), None, stream(cuda)),
+              "rows_convert_h16")
+        got16 = _dense(y.index.coords.cpu().numpy()[:n], back.cpu().numpy()[:n], B, y.index.spatial)
+        rel_check('narrow h16 rows wm=%d %d->%d' % (wm, cin, cout), got16, want)
+
+
 def test_strided_overflow_is_flagged(cuda):
     from paddle3d_b200.ops import sparse_nn as sp
     rng = np.random.default_rng(0)
