@@ -296,14 +296,18 @@ int p3d_sparse_conv_f16(const void *in_h16, const int32_t *nbr, const int32_t *n
  * H16 rows in and out, same fused epilogue and the same three-product arithmetic as p3d_sparse_conv_f16; only the weight
  * image differs (mma.sync fragment order, k permuted so that a lane's fragment is 4 contiguous channels of a row).
  * Missing neighbours cost nothing here (predicated-off loads), which is what bounds the tcgen05 kernel at these widths.
+ * Work is cut stream-K style into equal (tile, tap) ranges per warp; a tile cut by a range boundary is summed by the last
+ * warp to finish it, pieces in warp order (deterministic).  workspace = p3d_sparse_conv_wm_workspace_bytes(...) bytes whose
+ * first align_up(ceil(n_out_cap / 16) * 4) bytes (tickets) must be ZERO on first use (the kernel leaves them zero).
  * p3d_sparse_conv_wm_packed_weight_bytes returns 0 for unsupported shapes. */
 size_t p3d_sparse_conv_wm_packed_weight_bytes(int K, int Cin, int Cout);
 int p3d_sparse_conv_wm_pack_weights(const float *weight, int K, int Cin, int Cout, void *packed, int32_t *status_dev,
                                     p3d_stream_t stream);
+size_t p3d_sparse_conv_wm_workspace_bytes(int64_t n_out_cap, int Cout);
 int p3d_sparse_conv_wm(const void *in_h16, const int32_t *nbr, const int32_t *n_out_dev, int64_t n_out_cap, int K, int Cin,
                        int Cout, const void *packed_weight, const float *scale, const float *shift,
-                       const void *residual_h16, int relu, float *out_f32, void *out_h16, int32_t *status_dev,
-                       p3d_stream_t stream);
+                       const void *residual_h16, int relu, float *out_f32, void *out_h16, void *workspace,
+                       size_t workspace_bytes, int32_t *status_dev, p3d_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * SURVEY.md 8f-1 (parity-green, performance not measured yet): dense 2-D convolution on tcgen05 for the RPN / neck /

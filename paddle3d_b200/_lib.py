@@ -70,7 +70,9 @@ SIGNATURES = {
                                    _int, _vp, _vp]),
     "p3d_sparse_conv_wm_packed_weight_bytes": (_sz, [_int, _int, _int]),
     "p3d_sparse_conv_wm_pack_weights": (_int, [_vp, _int, _int, _int, _vp, _vp, _vp]),
-    "p3d_sparse_conv_wm": (_int, [_vp, _vp, _vp, _i64, _int, _int, _int, _vp, _vp, _vp, _vp, _int, _vp, _vp, _vp, _vp]),
+    "p3d_sparse_conv_wm_workspace_bytes": (_sz, [_i64, _int]),
+    "p3d_sparse_conv_wm": (_int, [_vp, _vp, _vp, _i64, _int, _int, _int, _vp, _vp, _vp, _vp, _int, _vp, _vp, _vp, _sz,
+                                  _vp, _vp]),
     "p3d_nchw_to_pixel_split": (_int, [_vp, _int, _int, _int, _int, _vp, _vp]),
     "p3d_dense_conv2d_packed_weight_bytes": (_sz, [_int, _int, _int, _int]),
     "p3d_pillar_feature_net": (_int, [_vp, _vp, _vp, _vp, _i64, _int, _int, _int, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),

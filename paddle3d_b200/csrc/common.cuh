@@ -38,10 +38,13 @@ struct Carver {
 };
 
 inline unsigned int div_up(long long a, long long b) { return static_cast<unsigned int>((a + b - 1) / b); }
+// Smallest power of two >= x, saturating at 2^31 (computed in 64 bits: a 32-bit accumulator wraps to 0 for x > 2^31 and
+// the loop never ends - ADVICE r1).  Callers reject row counts above kMaxRows before sizing a table with it.
+constexpr int64_t kMaxRows = 1ll << 29;  // hash tables hold 2x the rows: 2^30 64-bit entries at most
 inline uint32_t next_pow2(uint64_t x) {
-  uint32_t p = 1;
-  while (p < x) p <<= 1;
-  return p;
+  uint64_t p = 1;
+  while (p < x && p < (1ull << 31)) p <<= 1;
+  return static_cast<uint32_t>(p);
 }
 
 constexpr int kNumSMs = 148;  // B200

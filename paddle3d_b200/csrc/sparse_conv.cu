@@ -503,7 +503,7 @@ int make_dims(int batch, const int *sp, const int *ks, const int *st, const int 
 using namespace p3d;
 
 extern "C" size_t p3d_sparse_rulebook_workspace_bytes(int64_t n_in_cap, int64_t n_out_cap) {
-  if (n_in_cap < 0 || n_out_cap < 0) return 0;
+  if (n_in_cap < 0 || n_out_cap < 0 || n_in_cap > kMaxRows || n_out_cap > kMaxRows) return 0;
   return carve_rb(nullptr, n_in_cap, n_out_cap).bytes;
 }
 
@@ -640,6 +640,7 @@ struct Tab {
   uint32_t cap, shift;
 };
 bool tab_of(void *mem, size_t bytes, int64_t rows_cap, Tab *t) {
+  if (rows_cap > kMaxRows) return false;
   t->cap = next_pow2(static_cast<uint64_t>(rows_cap > 512 ? rows_cap : 512) * 2);
   t->shift = 32;
   for (uint32_t x = t->cap; x > 1; x >>= 1) --t->shift;
@@ -649,7 +650,7 @@ bool tab_of(void *mem, size_t bytes, int64_t rows_cap, Tab *t) {
 }  // namespace
 
 extern "C" size_t p3d_sparse_table_bytes(int64_t rows_cap) {
-  if (rows_cap < 0) return 0;
+  if (rows_cap < 0 || rows_cap > kMaxRows) return 0;
   return align_up(static_cast<size_t>(next_pow2(static_cast<uint64_t>(rows_cap > 512 ? rows_cap : 512) * 2)) * 8);
 }
 

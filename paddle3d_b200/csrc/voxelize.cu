@@ -382,7 +382,8 @@ __global__ void __launch_bounds__(256) voxel_mean_kernel(const float *__restrict
 }
 
 int check_geom(const float *vs, const float *pcr, int64_t n, int F, int P, int V, VoxGeom *g) {
-  if (!vs || !pcr || n < 0 || n > INT_MAX - kScanTile || F < 3 || P < 1 || V < 1) return P3D_ERR_INVALID_ARG;
+  if (!vs || !pcr || n < 0 || F < 3 || P < 1 || V < 1) return P3D_ERR_INVALID_ARG;
+  if (n > kMaxRows) return P3D_ERR_UNSUPPORTED;  // the cell hash holds 2 n entries (next_pow2 saturates beyond 2^31)
   g->min_x = pcr[0];
   g->min_y = pcr[1];
   g->min_z = pcr[2];
@@ -424,7 +425,7 @@ int run_front(const float *points, int n, int F, const VoxGeom &g, int P, int V,
 using namespace p3d;
 
 extern "C" size_t p3d_hard_voxelize_workspace_bytes(int64_t num_points, int max_points, int max_voxels) {
-  if (num_points < 0 || max_points < 1 || max_voxels < 1) return 0;
+  if (num_points < 0 || num_points > kMaxRows || max_points < 1 || max_voxels < 1) return 0;
   return carve(nullptr, num_points, max_points, max_voxels).bytes;
 }
 

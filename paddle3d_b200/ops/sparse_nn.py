@@ -259,9 +259,12 @@ def _run(p, t, want):
         if PROFILE is not None:
             s_ev.record(st)
         if p.wm:
+            wsb = L.p3d_sparse_conv_wm_workspace_bytes(p.cap, p.cout)
+            # one scratch buffer per (capacity, channels): its head holds the self-cleaning stream-K tickets (zero on creation)
+            ws = workspace(wsb, dev, "wm_streamk_%d_%d" % (p.cap, p.cout), zero=True)
             check(L.p3d_sparse_conv_wm(ptr(xin), ptr(p.nbr), ptr(p.num), p.cap, p.K, p.cin, p.cout, ptr(p.weight),
                                        ptr(p.scale), ptr(p.shift), ptr(res), int(p.relu), ptr(out_f32), ptr(out_h16),
-                                       ptr(status_tensor(dev)), stream(dev)), "sparse_conv_wm")
+                                       ptr(ws), wsb, ptr(status_tensor(dev)), stream(dev)), "sparse_conv_wm")
             t._vals[ROWS_F32], t._vals[ROWS_H16] = out_f32, out_h16
             if PROFILE is not None:
                 e_ev.record(st)

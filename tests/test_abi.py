@@ -39,6 +39,15 @@ def test_status_strings_and_size_queries():
     assert L.p3d_scatter_dense_workspace_bytes(1, 1, 496, 432) >= 496 * 432 * 4
     assert L.p3d_centerpoint_postprocess_workspace_bytes(6, 180, 180, 1000, 83) > 0
     assert L.p3d_sparse_rulebook_workspace_bytes(160000, 640000) > 0
+    # capacities whose hash table (2x rows, power of two) would not fit 2^31 entries are refused, not looped on
+    assert L.p3d_hard_voxelize_workspace_bytes(2 ** 31, 10, 10) == 0
+    assert L.p3d_sparse_table_bytes(2 ** 31 + 5) == 0
+    assert L.p3d_sparse_rulebook_workspace_bytes(2 ** 31, 16) == 0
+    # the narrow-layer warp-MMA kernel: supported shapes only
+    assert L.p3d_sparse_conv_wm_packed_weight_bytes(27, 16, 16) == 27 * 1024
+    assert L.p3d_sparse_conv_wm_packed_weight_bytes(27, 32, 32) == 27 * 4 * 1024
+    assert L.p3d_sparse_conv_wm_packed_weight_bytes(27, 64, 64) == 0
+    assert L.p3d_sparse_conv_wm_workspace_bytes(1000, 16) > 0
 
 
 def test_host_mirror_rejects_cpu_tensors():

@@ -35,7 +35,11 @@ def timed(fn, iters, flush):
         with torch.cuda.graph(g, stream=st):
             fn()
         for _ in range(iters):
-            flush.zero_()
+            # the flush is also what keeps the GPU busy while the host enqueues event + graph launch: with one 256 MB
+            # write (~45 us) the replay could arrive after the start event had fired, and every op measured >= ~57 us
+            # (round-2 finding); three writes give the host ~150 us of slack
+            for _ in range(3):
+                flush.zero_()
             s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             s.record(st)
             g.replay()
