@@ -525,16 +525,21 @@ def main():
         nvox = int(nv.item())
         tc_ms, tc_flops = 0.0, 0.0
         tcp = (sp.TF32X3, sp.TF32X3_SPLIT, sp.TF32X3_TMA, sp.F16X3)
-        for (cin, cout, K, prec, nbr, num, s_ev, e_ev) in prof:
+        wm_ms = 0.0
+        for (cin, cout, K, prec, nbr, num, s_ev, e_ev, kern) in prof:
             rows = int(num[0].item()) if num is not None else nbr.shape[0]
             pairs = int((nbr[:rows] >= 0).sum().item())
             ms = s_ev.elapsed_time(e_ev)
             fl = 2.0 * pairs * cin * cout
             layers.append({"cin": cin, "cout": cout, "rows": rows, "pairs": pairs, "ms": round(ms, 4),
-                           "precision": {sp.F16X3: "f16x3", sp.FP32: "fp32"}.get(prec, "tf32x3"), "gflop": round(fl / 1e9, 3)})
+                           "precision": {sp.F16X3: "f16x3", sp.FP32: "fp32"}.get(prec, "tf32x3"), "gflop": round(fl / 1e9, 3),
+                           "kernel": ("wm::conv_wm_kernel (register gather + mma.sync)" if kern == "wm" else
+                                      "tcgen05" if prec in tcp else "small_cin (fp32 FMA)")})
             if prec in tcp:
                 tc_ms += ms
                 tc_flops += fl
+                if kern == "wm":
+                    wm_ms += ms
         extra["stage_ms_eager"] = stage
         extra["num_voxels_frame0"] = nvox
         extra["sparse_conv_layers"] = layers
@@ -551,13 +556,16 @@ def main():
         if tc_ms > 0:
             ach = tc_flops / (tc_ms * 1e-3) / 1e12
             kname = {sp.F16X3: "f16::conv_f16_kernel", sp.TF32X3_SPLIT: "tc2::gather_gemm_split_kernel"}.get(precision, "tc::gather_gemm_tf32x3_kernel")
+            if wm_ms > 0:
+                kname += " (wide layers) + wm::conv_wm_kernel (16/32-channel layers, %.3f ms)" % wm_ms
             sparse_roof = {"bound": "tensor", "kernel": kname + " (the 20 tensor-core sparse convs of one frame)",
                            "achieved": ach, "peak": bf16_peak, "unit": "TFLOP/s", "frac": ach / bf16_peak,
                            "traffic": ncu_dram_bytes("r02_f16_ncu_metrics.csv"), "algorithmic_flops": tc_flops, "ms": tc_ms,
                            "peak_source": tpeak_src,
-                           "note": "achieved counts ALGORITHMIC flops 2*pairs*Cin*Cout; the kernel executes 3 fp16 MMAs per "
-                                   "product on zero-padded 128-row tiles; bound by the row gather (L1TEX wavefronts per gathered "
-                                   "row, profiles/r02_f16_probe.md), not by the tensor pipe"}
+                           "note": "achieved counts ALGORITHMIC flops 2*pairs*Cin*Cout; the kernels execute 3 fp16 MMAs per "
+                                   "product on zero-padded row tiles; bound by the row gather (tcgen05 kernel: L1TEX wavefronts "
+                                   "per gathered row, profiles/r02_f16_sweep.md; warp-MMA kernel: L2 latency of the register "
+                                   "gather + issue slots, profiles/r02_wm_ncu_metrics.csv), not by the tensor pipe"}
         dense_roof = None
         if pipe.dense is not None:
             if pipe.out["bev_h16"] is not None:

@@ -238,7 +238,7 @@ class _Pending:
                  "ready", "wm")
 
 
-PROFILE = None  # set to a list to record (cin, cout, K, precision, nbr, num, start_event, end_event) per conv launch
+PROFILE = None  # set to a list to record (cin, cout, K, precision, nbr, num, start_event, end_event, kernel) per conv launch
 
 
 def _run(p, t, want):
@@ -268,7 +268,7 @@ def _run(p, t, want):
             t._vals[ROWS_F32], t._vals[ROWS_H16] = out_f32, out_h16
             if PROFILE is not None:
                 e_ev.record(st)
-                PROFILE.append((p.cin, p.cout, p.K, p.precision, p.nbr, p.num, s_ev, e_ev))
+                PROFILE.append((p.cin, p.cout, p.K, p.precision, p.nbr, p.num, s_ev, e_ev, "wm"))
             return
         wsb = L.p3d_sparse_conv_f16_workspace_bytes(p.cap, p.cout, F16_MAX_SPLITS)
         # one scratch buffer per (capacity, channels): its head holds the self-cleaning split-K tickets (zero on creation)
@@ -328,7 +328,7 @@ def _run(p, t, want):
         t._vals[ROWS_F32] = out
     if PROFILE is not None:
         e_ev.record(st)
-        PROFILE.append((p.cin, p.cout, p.K, p.precision, p.nbr, p.num, s_ev, e_ev))
+        PROFILE.append((p.cin, p.cout, p.K, p.precision, p.nbr, p.num, s_ev, e_ev, "tc"))
 
 
 def _affine_act(x, scale, shift, residual, relu):

