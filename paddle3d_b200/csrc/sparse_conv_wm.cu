@@ -504,7 +504,7 @@ extern "C" int p3d_sparse_conv_wm(const void *in_h16, const int32_t *nbr, const 
   p.slabs = reinterpret_cast<float *>(static_cast<char *>(workspace) + align_up(static_cast<size_t>((n_out_cap + 15) / 16) * sizeof(int32_t)));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   static const int d_env = getenv("P3D_WM_D") ? atoi(getenv("P3D_WM_D")) : 0;  // tuning hook: ring depth
-  if (Cin == 16 && Cout == 16) {
+  if (Cin == 16 && Cout == 16) {  // measured per level-0 layer: D = 3 25.5 us, D = 5 25.0 us, D = 9 27.0 us
     if (d_env == 3) return wm::launch<16, 16, 3>(p, st);
     if (d_env == 9) return wm::launch<16, 16, 9>(p, st);
     return wm::launch<16, 16, 5>(p, st);
@@ -514,9 +514,9 @@ extern "C" int p3d_sparse_conv_wm(const void *in_h16, const int32_t *nbr, const 
     if (d_env == 9) return wm::launch<16, 32, 7>(p, st);
     return wm::launch<16, 32, 5>(p, st);
   }
-  if (Cin == 32 && Cout == 32) {
-    if (d_env == 3) return wm::launch<32, 32, 3>(p, st);
-    return wm::launch<32, 32, 4>(p, st);
+  if (Cin == 32 && Cout == 32) {  // measured: D = 3 33.4 us, D = 4 (8 bytes of spills) 35.4 us per level-1 layer
+    if (d_env == 4) return wm::launch<32, 32, 4>(p, st);
+    return wm::launch<32, 32, 3>(p, st);
   }
   return P3D_ERR_UNSUPPORTED;
 }

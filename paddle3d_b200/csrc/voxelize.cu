@@ -3,7 +3,7 @@
 // Replaces the reference's 7-kernel + cumsum pipeline over three dense 332 MB grids
 // (paddle3d/ops/voxel/voxelize_op.cu:208-346) with a hash of the occupied cells only:
 //
-//   K0 vox_init        table <- EMPTY, scan descriptors <- 0, slot lists <- INF           (one launch)
+//   K0 vox_init        table <- EMPTY, scan descriptors / voxel counts <- 0, overflow lists <- INF   (one launch)
 //   K1 vox_insert      per point: cell id, open-addressing insert; the 64-bit entry is
 //                      (cell << 32 | point index) and is reduced with one atomicMin, so each
 //                      occupied cell ends up holding its FIRST point — the quantity the CPU
@@ -12,16 +12,19 @@
 //                      lowest lane (smallest index) touches the table.
 //   K2 vox_rank        single-pass decoupled-look-back scan over "is first point of its cell"
 //                      flags -> voxel id (rank < max_voxels, else dropped: .cc:61-64), coords.
-//   K3 vox_slots       per point: keep the max_points smallest point indices of its voxel, in
-//                      ascending order, with a cascade of atomicMin (deterministic under any
-//                      interleaving: slot s always converges to the (s+1)-th smallest index)
-//                      — the CPU kernel's "first P points in input order" (.cc:71-79).
+//   K3 vox_slots       per point: arrival number inside its voxel (one atomicAdd); the first C arrivals are recorded
+//                      as they come, later ones (voxels with more than C = max(4P, 32) points; for P > 16 every point takes this path, see cand_slots) keep their P smallest
+//                      indices with a cascade of atomicMin (deterministic under any interleaving: slot s always
+//                      converges to the (s+1)-th smallest index).
+//   K3b vox_select     per (voxel, slot): the P smallest recorded indices in ascending order - the CPU kernel's
+//                      "first P points in input order" (.cc:71-79) - by rank counting (indices are distinct).
 //   K4 vox_write       gather-formulated single pass over the outputs: every float4 of
 //                      voxels[max_voxels, P, F] is written exactly once (point value or zero),
 //                      coalesced, plus num_points_per_voxel and the zero tail of coords.
 //                      This is the HBM-roofline kernel: 4NF + 4VPF + 12V + 4V algorithmic bytes.
 //
-// All intermediate state (<= 8*cap + 4*(N + cap + V*P) bytes) is L2-resident on B200.
+// All intermediate state (8*cap + 4*(N + cap + V*(2P + C + 1)) bytes, of which only the rows of live voxels are touched)
+// is L2-resident on B200.
 #include <limits.h>
 
 #include "common.cuh"
@@ -46,11 +49,27 @@ struct VoxWs {
   unsigned long long *desc;    // [nblocks + 1]  desc[0] = ticket, desc[1 + b] = (status << 32 | value)
   int32_t *pt_slot;            // [N] table slot of each point, -1 = outside the grid
   int32_t *slot_vox;           // [cap] voxel id of an occupied slot (-1 = beyond max_voxels)
-  int32_t *lists;              // [V, P] the P smallest point indices of each voxel, ascending
+  int32_t *lists;              // [V, P] the P smallest point indices of each voxel, ascending (written by K3b)
+  int32_t *count;              // [V] points of each voxel (zeroed by K0)
+  int32_t *cand;               // [V, C] point indices in ARRIVAL order, the first C arrivals of each voxel (K3)
+  int32_t *ovf;                // [V, P] P smallest indices among the arrivals beyond C (atomicMin cascade), INF-filled by K0
+  int C;                       // candidate slots per voxel
   uint32_t cap, shift;
   unsigned int nblocks;
   size_t bytes;
 };
+
+// Candidate slots per voxel: a voxel's first C points (in arrival order) are kept as they come, one atomicAdd each;
+// only voxels with more than C points fall back to the atomicMin cascade for the rest.
+inline int cand_slots(int P) {
+  // Measured (B200): recording arrivals costs one same-address atomicAdd per point of a voxel and the selection is
+  // quadratic in the voxel's population; it wins for the small P of the voxel models (C3, P = 10: K3 + K3b 13 us
+  // against 27 us for the all-cascade K3) and loses for pillar models (C2, P = 32, pillars of 200 points: 44 us
+  // against 36 us).  C = 0 selects the all-cascade path: K3 cascades every point into `ovf`, which K4 reads directly.
+  if (P > 16) return 0;
+  int c = 4 * P > 32 ? 4 * P : 32;
+  return (c + 3) & ~3;
+}
 
 VoxWs carve(void *ws, int64_t n, int P, int V) {
   VoxWs w;
@@ -63,14 +82,18 @@ VoxWs carve(void *ws, int64_t n, int P, int V) {
   w.desc = c.take<unsigned long long>(w.nblocks + 1);
   w.pt_slot = c.take<int32_t>(n > 0 ? n : 1);
   w.slot_vox = c.take<int32_t>(w.cap);
-  w.lists = c.take<int32_t>(static_cast<size_t>(V) * P);
+  w.C = cand_slots(P);
+  w.count = c.take<int32_t>(static_cast<size_t>(V));
+  w.cand = c.take<int32_t>(static_cast<size_t>(V) * (w.C > 0 ? w.C : 1));
+  w.ovf = c.take<int32_t>(static_cast<size_t>(V) * P);
+  w.lists = w.C > 0 ? c.take<int32_t>(static_cast<size_t>(V) * P) : w.ovf;  // all-cascade path: the cascade's lists are final
   w.bytes = c.off;
   return w;
 }
 
 // ---------------------------------------------------------------- K0
 __global__ void vox_init_kernel(uint4 *table16, size_t n_table16, uint4 *desc16, size_t n_desc16, uint4 *lists16,
-                                size_t n_lists16) {
+                                size_t n_lists16, uint4 *count16, size_t n_count16) {
   pdl_trigger();
   pdl_wait();
   const size_t stride = static_cast<size_t>(gridDim.x) * blockDim.x;
@@ -81,6 +104,7 @@ __global__ void vox_init_kernel(uint4 *table16, size_t n_table16, uint4 *desc16,
   for (size_t i = tid; i < n_table16; i += stride) table16[i] = ones;
   for (size_t i = tid; i < n_desc16; i += stride) desc16[i] = zero;
   for (size_t i = tid; i < n_lists16; i += stride) lists16[i] = inf;
+  for (size_t i = tid; i < n_count16; i += stride) count16[i] = zero;
 }
 
 // ---------------------------------------------------------------- K1
@@ -248,8 +272,9 @@ __global__ void __launch_bounds__(kScanBlock) vox_rank_kernel(const unsigned lon
 
 // ---------------------------------------------------------------- K3
 __global__ void __launch_bounds__(256) vox_slots_kernel(const int32_t *__restrict__ pt_slot,
-                                                        const int32_t *__restrict__ slot_vox, int n, int P,
-                                                        int32_t *__restrict__ lists) {
+                                                        const int32_t *__restrict__ slot_vox, int n, int P, int C,
+                                                        int32_t *__restrict__ count, int32_t *__restrict__ cand,
+                                                        int32_t *__restrict__ ovf) {
   pdl_trigger();
   pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -258,16 +283,21 @@ __global__ void __launch_bounds__(256) vox_slots_kernel(const int32_t *__restric
   if (slot < 0) return;
   const int v = slot_vox[slot];
   if (v < 0) return;
-  int32_t *L = lists + static_cast<size_t>(v) * P;
-  // Measured (round 2, C3 frame: 38 % of the points sit in the 7 153 voxels that hold more than P = 10 points, at most
-  // 42): this kernel is bound by the serialisation of same-line atomics inside those voxels (~c x P/2 dependent L2
-  // round trips for a voxel of c points; warps active < 10 %).  A per-voxel upper bound on the P-th smallest index
-  // (minimum of each residue class i % P, one more launch) was tried: it removes candidates only in voxels far above
-  // 3 P points, which this cloud does not have, and cost 6 us for nothing.
-  // Every list entry only ever decreases.  So (a) once the LAST entry is below i, i can never be among the P smallest:
-  // one read retires almost every point of an over-full cell (the hot cells of a dense cloud used to serialise
-  // P atomics per point); (b) the levels whose entry is already below i can be skipped, and reading them all at
-  // once (independent loads, one L2 round trip) instead of one dependent read per level shortens the chain.
+  // One atomic per point: arrival number inside the voxel.  The first C arrivals are simply recorded (K3b orders them);
+  // measured on the C3 frame, where 38 % of the points sit in voxels of 11 .. 42 points, the earlier all-cascade version
+  // spent 27 us serialising ~c x P / 2 dependent same-line atomics per such voxel.
+  if (C > 0) {
+    const int a = atomicAdd(count + v, 1);
+    if (a < C) {
+      cand[static_cast<size_t>(v) * C + a] = i;
+      return;
+    }
+  }
+  // Voxels with more than C points (dense clusters): the P smallest indices of the overflow arrivals, by a cascade of
+  // atomicMin - slot s converges to the (s+1)-th smallest under any interleaving.  Every entry only ever decreases, so
+  // once the LAST entry is below i, i can never be among the P smallest, and the leading levels already below i are
+  // skipped after one round of independent loads.
+  int32_t *L = ovf + static_cast<size_t>(v) * P;
   if (__ldcg(L + P - 1) < i) return;
   int s = 0;
   for (int s0 = 0; s0 < P; s0 += 8) {
@@ -288,6 +318,41 @@ __global__ void __launch_bounds__(256) vox_slots_kernel(const int32_t *__restric
     const int old = atomicMin(&L[s], cur);
     if (old == kInf) break;     // landed in a free slot
     if (old > cur) cur = old;   // displaced a larger index: carry it down
+  }
+}
+
+// ---------------------------------------------------------------- K3b
+// lists[v][0..P) = the P smallest point indices of voxel v in ascending order (INF padding) - the CPU kernel's "first P
+// points in input order" (voxelize_op.cc:71-79) - selected from the recorded arrivals (plus, for voxels beyond C points,
+// the cascade's P survivors: the P smallest overall are among the first C arrivals or the P smallest of the rest).
+// One thread per (voxel, slot): it ranks its share of the candidates (indices are distinct, so ranks are unique) and
+// stores each candidate of rank < P at lists[v][rank]; slots no candidate reaches get INF.
+__global__ void __launch_bounds__(256) vox_select_kernel(const int32_t *__restrict__ count, const int32_t *__restrict__ cand,
+                                                         const int32_t *__restrict__ ovf, int V, int P, int C,
+                                                         int32_t *__restrict__ lists) {
+  pdl_trigger();
+  pdl_wait();
+  const long long q = static_cast<long long>(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (q >= static_cast<long long>(V) * P) return;
+  const int v = static_cast<int>(q / P), s = static_cast<int>(q - static_cast<long long>(v) * P);
+  const int cnt = __ldg(count + v);
+  const int m = cnt < C ? cnt : C;
+  const int total = m + (cnt > C ? P : 0);
+  const int32_t *cv = cand + static_cast<size_t>(v) * C, *ov = ovf + static_cast<size_t>(v) * P;
+  if (s >= (cnt < P ? cnt : P)) lists[q] = kInf;  // cnt > C >= P: every slot is reached
+  // (both arrays were completed by the previous launch: read-only loads, four comparisons in flight)
+  for (int j = s; j < total; j += P) {
+    const int x = j < m ? __ldg(cv + j) : __ldg(ov + (j - m));
+    if (x == kInf) continue;
+    int rank = 0;
+    int k = 0;
+    for (; k + 4 <= m; k += 4) {
+      const int4 c4 = __ldg(reinterpret_cast<const int4 *>(cv + k));  // C is a multiple of 4, rows are 16-byte aligned
+      rank += (c4.x < x) + (c4.y < x) + (c4.z < x) + (c4.w < x);
+    }
+    for (; k < m; ++k) rank += (__ldg(cv + k) < x) ? 1 : 0;
+    for (k = m; k < total; ++k) rank += (__ldg(ov + (k - m)) < x) ? 1 : 0;
+    if (rank < P) lists[static_cast<size_t>(v) * P + rank] = x;
   }
 }
 
@@ -411,16 +476,21 @@ int run_front(const float *points, int n, int F, const VoxGeom &g, int P, int V,
   const size_t n_d16 = (static_cast<size_t>(w.nblocks) + 1 + 1) / 2;  // carve() pads to 256 B
   const size_t n_l16 = (static_cast<size_t>(V) * P + 3) / 4;
   P3D_CUDA_CHECK(launch_pdl(vox_init_kernel, dim3(kNumSMs * 4), dim3(256), 0, st, reinterpret_cast<uint4 *>(w.table), n_t16,
-                            reinterpret_cast<uint4 *>(w.desc), n_d16, reinterpret_cast<uint4 *>(w.lists), n_l16));
+                            reinterpret_cast<uint4 *>(w.desc), n_d16, reinterpret_cast<uint4 *>(w.ovf), n_l16,
+                            reinterpret_cast<uint4 *>(w.count), (static_cast<size_t>(V) + 3) / 4));
   if (n > 0) {
     P3D_CUDA_CHECK(launch_pdl(vox_insert_kernel, dim3(div_up(n, 256)), dim3(256), 0, st, points, n, F, g, w.table,
                               w.cap - 1, w.shift, w.pt_slot));
     P3D_CUDA_CHECK(launch_pdl(vox_rank_kernel, dim3(w.nblocks), dim3(kScanBlock), 0, st, w.table, w.pt_slot, n, V, g, w.desc,
                               w.slot_vox, coords, coord_stride, coord_off, batch_id, num_voxels));
-    P3D_CUDA_CHECK(launch_pdl(vox_slots_kernel, dim3(div_up(n, 256)), dim3(256), 0, st, w.pt_slot, w.slot_vox, n, P, w.lists));
+    P3D_CUDA_CHECK(launch_pdl(vox_slots_kernel, dim3(div_up(n, 256)), dim3(256), 0, st, w.pt_slot, w.slot_vox, n, P, w.C,
+                              w.count, w.cand, w.ovf));
   } else {
     P3D_CUDA_CHECK(cudaMemsetAsync(num_voxels, 0, sizeof(int32_t), st));
   }
+  if (w.C > 0)
+    P3D_CUDA_CHECK(launch_pdl(vox_select_kernel, dim3(div_up(static_cast<long long>(V) * P, 256)), dim3(256), 0, st, w.count, w.cand,
+                              w.ovf, V, P, w.C, w.lists));
   return P3D_OK;
 }
 
