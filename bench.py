@@ -12,10 +12,14 @@ Headline geometry: 0.075 m voxels / +-54 m (the heavier one); the 0.1 m / +-72 m
 measured in the same run and reported under `geometry_01m` (--geometry 01 swaps them).  --no-head reproduces the
 round-1 workload (resident synthetic head tensors).
 
-`value`  : frames/s with the frame's points already resident in HBM (CUDA-graph replay per frame).
-`e2e`    : frames/s through the public API CenterPointHotPath.infer_many(): pinned-host points -> H2D ->
-           graph -> D2H of boxes/scores/labels/counts/status, every step; the H2D of frame i+1 overlaps the compute of
-           frame i (copy stream + two staging buffers). `e2e.sync_value` is the one-frame-at-a-time infer() rate.
+`value`  : frames/s with the frame's points already resident in HBM (CUDA-graph replay per frame), --in-flight frames
+           (default 3) computing concurrently per GPU: CenterPointSweep lanes with their own buffers / graph / stream and a
+           shared model (measured: 605 / 709 / 739 frames/s with 1 / 2 / 3 lanes - the latency-bound kernels of one frame
+           fill the SMs the other frames leave idle).
+`e2e`    : frames/s through the public API CenterPointSweep.infer_many(): pinned-host points -> H2D ->
+           graph -> D2H of boxes/scores/labels/counts/status, every step; the H2D of a lane's next frame overlaps its
+           compute (copy stream + two staging buffers per lane). `e2e.sync_value` is the one-frame-at-a-time
+           CenterPointHotPath.infer() rate (latency mode, one lane).
 `roofline`: the kernel family with the largest share of the frame (dense conv or sparse conv), `rooflines_other` the
            rest; timed live with CUDA events on the launching stream.
 N > 1: frame-parallel replicas, one process per GPU (torchrun), weights broadcast once over NCCL,
@@ -44,11 +48,12 @@ BN_GAIN = 6.0 ** 0.5  # seeded weights with BatchNorm gamma = sqrt(6): activatio
 POOL = 32  # distinct frames cycled through: 32 x 6 MB = 192 MB of inputs > 126 MB L2
 
 
-def make_config(geometry, with_head):
+def make_config(geometry, with_head, in_flight=3):
     """The `config` object both arms print (identical dicts: the driver compares them)."""
     geo = "0.075 m voxels / +-54 m range" if geometry == "0075" else "0.1 m voxels / +-72 m range"
     return {"workload": WORKLOAD % (geo, HEAD_ON if with_head else HEAD_OFF), "geometry": geometry, "with_head": bool(with_head),
-            "frames_in_pool": POOL, "l2": "input pool 192 MB > 126 MB L2; no explicit flush"}
+            "frames_in_pool": POOL, "l2": "input pool 192 MB > 126 MB L2; no explicit flush",
+            "frames_in_flight_per_gpu": int(in_flight)}
 
 
 def frame_pool(cfg, n_frames, seed0=0, base=4):
@@ -191,7 +196,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": n_warm, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32 (f64 accumulation)", "data": "synthetic",
-            "config": make_config(args.geometry, with_head),
+            "config": make_config(args.geometry, with_head, max(1, args.in_flight)),
             "cpu_baseline": {"value": fps, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "stage_ms": {k: 1e3 * v / args.steps for k, v in stages.items()}, "gpu_launches": 0,
@@ -263,15 +268,15 @@ def dense_flops(net, H, W):
     return total
 
 
-def measure(pipe, dev_frames, host_frames, args, world, dist, sample_clocks, local):
-    """Device-timed resident-input rate, e2e (pipelined and one-frame-at-a-time) for one pipeline.  Returns a dict."""
+def measure(sweep, dev_frames, host_frames, args, world, dist, sample_clocks, local):
+    """Device-timed resident-input rate, e2e (pipelined and one-frame-at-a-time) for one sweep engine (len(sweep) frames in
+    flight, CenterPointSweep).  Returns a dict."""
     import torch
+    pipe = sweep.lanes[0]
     st = pipe.stream
 
     def step_resident(i):
-        with torch.cuda.stream(st):
-            pipe.points.copy_(dev_frames[i % len(dev_frames)], non_blocking=True)  # D2D: the frame is already in HBM
-            pipe.graph.replay()
+        sweep.launch(i, dev_frames[i % len(dev_frames)])  # D2D copy (the frame is already in HBM) + graph replay on lane i % L
 
     def barrier():
         torch.cuda.synchronize()
@@ -291,22 +296,26 @@ def measure(pipe, dev_frames, host_frames, args, world, dist, sample_clocks, loc
     barrier()
     t0 = time.perf_counter()
     s.record(st)
+    for p in sweep.lanes[1:]:
+        p.stream.wait_event(s)   # every lane starts after the start event ...
     for i in range(args.steps):
         step_resident(i)
+    for p in sweep.lanes[1:]:
+        st.wait_stream(p.stream)  # ... and the end event fires after the last frame of every lane
     e.record(st)
     barrier()
     wall = time.perf_counter() - t0
     dev_ms = s.elapsed_time(e)
     # ---- e2e through the public API (host in, host out), same K
-    pipe.prepare_sweep()
+    sweep.prepare_sweep()
     for i in range(3):
         pipe.infer(host_frames[i % len(host_frames)])
-    for _res in pipe.infer_many(host_frames[i % len(host_frames)] for i in range(4)):  # untimed: first use of the sweep path
+    for _res in sweep.infer_many(host_frames[i % len(host_frames)] for i in range(4 * len(sweep))):  # untimed: first use of the sweep path
         pass
     barrier()
     t1 = time.perf_counter()
     n_res = 0
-    for _res in pipe.infer_many(host_frames[i % len(host_frames)] for i in range(args.steps)):  # per-frame H2D + D2H, pipelined
+    for _res in sweep.infer_many(host_frames[i % len(host_frames)] for i in range(args.steps)):  # per-frame H2D + D2H, pipelined
         n_res += 1
     assert n_res == args.steps
     barrier()
@@ -405,6 +414,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-head", action="store_true", help="skip the dense RPN / neck / CenterHead (round-1 workload)")
     ap.add_argument("--no-second-geometry", action="store_true")
+    ap.add_argument("--in-flight", type=int, default=3, help="frames computing concurrently per GPU (CenterPointSweep lanes)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
@@ -416,7 +426,7 @@ def main():
     from paddle3d_b200 import synth
     from paddle3d_b200.ops import sparse_nn as sp
     from paddle3d_b200.ops import voxelize as vox
-    from paddle3d_b200.pipeline import CenterPointHotPath
+    from paddle3d_b200.pipeline import CenterPointHotPath, CenterPointSweep
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -434,8 +444,10 @@ def main():
     precision = {"tf32x3": sp.TF32X3, "tf32x3_split": sp.TF32X3_SPLIT, "tf32x3_tma": sp.TF32X3_TMA, "fp32": sp.FP32,
                  "f16x3": sp.F16X3}[args.precision]
     caps = [int(x) for x in os.environ["P3D_LEVEL_CAPS"].split(",")] if os.environ.get("P3D_LEVEL_CAPS") else None
-    pipe = CenterPointHotPath(cfg, dev, precision=precision, seed=0, level_caps=caps, with_head=with_head, keep_bev=False,
-                              bn_gain=BN_GAIN)
+    lanes = max(1, args.in_flight)
+    sweep = CenterPointSweep(lanes, cfg=cfg, device=dev, precision=precision, seed=0, level_caps=caps, with_head=with_head,
+                             keep_bev=False, bn_gain=BN_GAIN)
+    pipe = sweep.lanes[0]  # the lanes share one model; lane 0 is the one the rooflines / checks below look at
     if world > 1:  # weights only: one broadcast over NVLink at start, no per-frame collective
         from paddle3d_b200.sharding import broadcast_weights
         broadcast_weights(pipe.net, 0)
@@ -446,17 +458,21 @@ def main():
     pipe.calibrate_head(dev_frames[0])   # random-init heat maps -> ~1.4 % of cells above the score threshold
     pipe.points.copy_(dev_frames[0])
     pipe.capture(count_nodes=rank == 0)
+    for p in sweep.lanes[1:]:
+        p.points.copy_(dev_frames[0])
+        p.capture()
     graph_nodes = pipe.graph_nodes["kernel"] if (rank == 0 and pipe.graph_nodes) else None
     st = pipe.stream
-    m = measure(pipe, dev_frames, host_frames, args, world, dist, True, local)
+    m = measure(sweep, dev_frames, host_frames, args, world, dist, True, local)
 
     # ---- the other geometry, same model, shorter run (reported, not the headline)
     other = None
     if not args.no_second_geometry:
         ogeo = "01" if args.geometry == "0075" else "0075"
         ocfg = synth.C3_01 if ogeo == "01" else synth.C3
-        opipe = CenterPointHotPath(ocfg, dev, precision=precision, seed=0, level_caps=caps, with_head=with_head, keep_bev=False,
-                                   bn_gain=BN_GAIN)
+        osweep = CenterPointSweep(lanes, cfg=ocfg, device=dev, precision=precision, seed=0, level_caps=caps, with_head=with_head,
+                                  keep_bev=False, bn_gain=BN_GAIN)
+        opipe = osweep.lanes[0]
         oframes = frame_pool(ocfg, 8, seed0=rank * 100, base=2)
         odev = [torch.from_numpy(f).to(dev) for f in oframes]
         ohost = [torch.from_numpy(f).pin_memory() for f in oframes]
@@ -464,12 +480,11 @@ def main():
             for ca, cb in zip(opipe.dense.all_convs(), pipe.dense.all_convs()):
                 ca.np["bias"] = cb.np["bias"]
             opipe.dense._batched = None
-        opipe.points.copy_(odev[0])
-        opipe.capture()
+        osweep.capture(odev[0])
         oargs = argparse.Namespace(steps=max(20, args.steps // 4), warmup=max(3, args.warmup // 4))
-        om = measure(opipe, odev, ohost, oargs, world, dist, False, local)
+        om = measure(osweep, odev, ohost, oargs, world, dist, False, local)
         other = (ogeo, om, oargs, int(opipe.out["num_voxels"][0].item()))
-        del opipe, odev, ohost
+        del osweep, opipe, odev, ohost
 
     # ---- rooflines of the dominant kernels, timed live (events on the launching stream), rank 0 only
     extra = {}
@@ -635,11 +650,13 @@ def main():
                 "warmup": args.warmup, "ms_per_step": m["ms_per_step"], "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None,
                 "dtype": {"fp32": "f32", "f16x3": "f16x3 (fp16 hi/lo' pairs, f32 accumulation)"}.get(args.precision, "tf32x3 (f32 accumulation)"),
-                "data": "synthetic", "config": make_config(args.geometry, with_head),
-                "parallelism": "frame-parallel x%d (replicas, NCCL weight broadcast only)" % world,
+                "data": "synthetic", "config": make_config(args.geometry, with_head, lanes),
+                "parallelism": "frame-parallel x%d (replicas, NCCL weight broadcast only), %d frames in flight per GPU "
+                               "(CenterPointSweep lanes: own buffers / graph / stream, shared model)" % (world, lanes),
                 "precision": args.precision,
                 "e2e": {"value": m["e2e_value"], "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "api": "CenterPointHotPath.infer_many (H2D of frame i+1 overlaps compute of frame i)",
+                        "api": "CenterPointSweep.infer_many (%d lanes; H2D of the next frame of a lane overlaps its compute)" % lanes,
+                        "sync_note": "sync_value = CenterPointHotPath.infer, one frame at a time (latency mode, one lane)",
                         "sync_value": m["e2e_sync_value"] if world == 1 else None},
                 "gpu_launches": per_frame_launches * args.steps,
                 "gpu_launches_per_step": per_frame_launches,
@@ -649,7 +666,7 @@ def main():
         if other is not None:
             ogeo, om, oargs, onv = other
             line["geometry_01m" if ogeo == "01" else "geometry_0075"] = {
-                "config": make_config(ogeo, with_head), "value": om["value"], "unit": UNIT, "ms_per_step": om["ms_per_step"],
+                "config": make_config(ogeo, with_head, lanes), "value": om["value"], "unit": UNIT, "ms_per_step": om["ms_per_step"],
                 "steps": oargs.steps, "warmup": oargs.warmup, "num_voxels_frame0": onv,
                 "e2e": {"value": om["e2e_value"], "unit": UNIT, "sync_value": om["e2e_sync_value"] if world == 1 else None}}
         line.update(extra)

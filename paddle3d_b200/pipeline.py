@@ -206,48 +206,50 @@ class CenterPointHotPath:
         self._done = [torch.cuda.Event() for _ in range(2)]      # results of slot k are on the host
         return self
 
+    def _submit(self, pts, k, first_use):
+        """Enqueue one frame of a sweep into slot k: H2D on the copy stream, graph replay, D2H of the results."""
+        cs, st = self._copy_stream, self.stream
+        with torch.cuda.stream(cs):
+            if not first_use:
+                cs.wait_event(self._consumed[k])
+            self._staging[k].copy_(pts, non_blocking=True)
+            self._staged[k].record(cs)
+        with torch.cuda.stream(st):
+            st.wait_event(self._staged[k])
+            self.points.copy_(self._staging[k], non_blocking=True)
+            self._consumed[k].record(st)
+            self.graph.replay()
+            o, sl = self.out, self._slots[k]
+            sl["counts"].copy_(o["counts"], non_blocking=True)
+            sl["status"].copy_(o["status"], non_blocking=True)
+            sl["boxes"].copy_(o["boxes"], non_blocking=True)
+            sl["scores"].copy_(o["scores"], non_blocking=True)
+            sl["labels"].copy_(o["labels"], non_blocking=True)
+            self._done[k].record(st)
+
+    def _result(self, k):
+        self._done[k].synchronize()
+        sl = self._slots[k]
+        self.check_status(sl["status"])
+        n = int(sl["counts"][-1])
+        return sl["boxes"][:n].clone(), sl["scores"][:n].clone(), sl["labels"][:n].clone()
+
     def infer_many(self, frames_host):
         """frames_host: iterable of pinned [n, F] fp32 tensors.  Yields (boxes, scores, labels) per frame, in order.
 
         Every frame still pays its own H2D copy and its own D2H read-back; the H2D of frame i+1 runs on a copy
         stream while frame i computes (two device staging buffers, two pinned result slots), and the host reads the
-        results of frame i after it has submitted frame i+1."""
+        results of frame i after it has submitted frame i+1.  CenterPointSweep runs several such lanes side by side."""
         if self.graph is None:
             raise RuntimeError("infer_many needs a captured pipeline: call capture() first")
         self.prepare_sweep()
-        cs, st = self._copy_stream, self.stream
-
-        def result(k):
-            self._done[k].synchronize()
-            sl = self._slots[k]
-            self.check_status(sl["status"])
-            n = int(sl["counts"][-1])
-            return sl["boxes"][:n].clone(), sl["scores"][:n].clone(), sl["labels"][:n].clone()
-
         i = -1
         for i, pts in enumerate(frames_host):
-            k = i & 1
-            with torch.cuda.stream(cs):
-                if i >= 2:
-                    cs.wait_event(self._consumed[k])
-                self._staging[k].copy_(pts, non_blocking=True)
-                self._staged[k].record(cs)
-            with torch.cuda.stream(st):
-                st.wait_event(self._staged[k])
-                self.points.copy_(self._staging[k], non_blocking=True)
-                self._consumed[k].record(st)
-                self.graph.replay()
-                o, sl = self.out, self._slots[k]
-                sl["counts"].copy_(o["counts"], non_blocking=True)
-                sl["status"].copy_(o["status"], non_blocking=True)
-                sl["boxes"].copy_(o["boxes"], non_blocking=True)
-                sl["scores"].copy_(o["scores"], non_blocking=True)
-                sl["labels"].copy_(o["labels"], non_blocking=True)
-                self._done[k].record(st)
+            self._submit(pts, i & 1, i < 2)
             if i >= 1:
-                yield result((i - 1) & 1)
+                yield self._result((i - 1) & 1)
         if i >= 0:
-            yield result(i & 1)
+            yield self._result(i & 1)
 
     def bytes_per_frame(self):
         h2d = self.n * self.F * 4
@@ -273,3 +275,77 @@ class CenterPointHotPath:
                     blocks0=[block(b) for b in n.blocks0],
                     stages=[dict(down=dict(conv=conv(d[0]), bn=bn(d[1])), blocks=[block(b) for b in bl]) for d, bl in n.stages],
                     extra=dict(conv=conv(n.extra_conv[0]), bn=bn(n.extra_conv[1])))
+
+
+class CenterPointSweep:
+    """Several frames of a sweep in flight on ONE GPU.
+
+    `lanes` CenterPointHotPath instances share the model (weights, packed images) but own their buffers, workspaces,
+    CUDA graph and stream; frames are dealt round-robin.  A frame is a chain of ~70 kernels of very different shapes -
+    persistent tensor-core kernels that fill the GPU, and latency-bound ones (voxel hashing, rulebooks, post-processing,
+    the tails of every layer) that leave most SMs idle: with a second frame in flight those gaps are filled by the other
+    frame's kernels.  Measured on the C3 frame (tools/two_in_flight.py): 602 -> 713 frames/s with two lanes.  The latency
+    of one frame does not improve (use CenterPointHotPath.infer for that); results are those of the single-lane pipeline.
+    """
+
+    def __init__(self, lanes=2, **kw):
+        if lanes < 1:
+            raise ValueError("lanes >= 1")
+        first = CenterPointHotPath(**kw)
+        self.lanes = [first]
+        for _ in range(lanes - 1):
+            p = CenterPointHotPath(**kw)
+            p.net, p.dense = first.net, first.dense  # one model: calibration / weight loading happens once, on lane 0
+            self.lanes.append(p)
+        self.device = first.device
+
+    def __len__(self):
+        return len(self.lanes)
+
+    def calibrate_head(self, points_dev):
+        self.lanes[0].calibrate_head(points_dev)
+        return self
+
+    def capture(self, points_dev, **kw):
+        for p in self.lanes:
+            p.points.copy_(points_dev)
+            p.capture(**kw)
+        return self
+
+    def prepare_sweep(self):
+        for p in self.lanes:
+            p.prepare_sweep()
+        return self
+
+    def launch(self, i, points_dev):
+        """Frame i of a device-resident sweep: copy into lane i % lanes and replay its graph (asynchronous)."""
+        p = self.lanes[i % len(self.lanes)]
+        with torch.cuda.stream(p.stream):
+            p.points.copy_(points_dev, non_blocking=True)
+            p.graph.replay()
+        return p
+
+    def synchronize(self):
+        for p in self.lanes:
+            p.stream.synchronize()
+
+    def infer_many(self, frames_host):
+        """As CenterPointHotPath.infer_many (pinned host frames in, host results out, in order), with len(self) frames
+        computing concurrently: frame i runs on lane i % lanes, slot (i // lanes) & 1."""
+        import collections
+        L = len(self.lanes)
+        for p in self.lanes:
+            if p.graph is None:
+                raise RuntimeError("infer_many needs captured lanes: call capture() first")
+            p.prepare_sweep()
+        pending = collections.deque()
+        for i, pts in enumerate(frames_host):
+            lane, k = self.lanes[i % L], (i // L) & 1
+            lane._submit(pts, k, i < 2 * L)
+            pending.append((lane, k))
+            if len(pending) > L:
+                pl, pk = pending.popleft()
+                yield pl._result(pk)
+        while pending:
+            pl, pk = pending.popleft()
+            yield pl._result(pk)

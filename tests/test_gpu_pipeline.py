@@ -156,3 +156,31 @@ def test_fused_pixel_h16_bev_matches_nchw_path(cuda):
     keep = rc[2].numpy() == rb[2].numpy()
     assert keep.mean() > 0.98
     assert np.abs(rc[0].numpy()[keep] - rb[0].numpy()[keep]).max() <= 1e-4 * max(1.0, float(rb[0].abs().max()))
+
+
+def test_sweep_lanes_match_single_lane(cuda):
+    """CenterPointSweep (two frames in flight: two lanes sharing one model, frames dealt round-robin) returns, in order,
+    what the single-lane pipeline returns for each frame of a sweep of distinct frames."""
+    import torch
+    from paddle3d_b200.pipeline import CenterPointSweep
+    frames = [torch.from_numpy(f).pin_memory() for f in _frames(5)]
+    single = _pipe(cuda, 4, with_head=True, keep_bev=False)
+    single.calibrate_head(frames[0].to(cuda))
+    single.points.copy_(frames[0].to(cuda))
+    single.capture()
+    want = list(single.infer_many(iter(frames)))
+    sweep = CenterPointSweep(2, cfg=synth.C3, device=cuda, precision=4, seed=3, num_points=N_POINTS, with_head=True, keep_bev=False)
+    assert sweep.lanes[1].net is sweep.lanes[0].net and sweep.lanes[1].dense is sweep.lanes[0].dense
+    sweep.calibrate_head(frames[0].to(cuda))
+    sweep.capture(frames[0].to(cuda))
+    got = list(sweep.infer_many(iter(frames)))
+    assert len(got) == len(want) == 5
+    counts = [len(w[2]) for w in want]
+    assert len(set(counts)) > 1 or counts[0] > 6  # the frames really differ / detect something
+    for g, w in zip(got, want):
+        assert len(g[2]) == len(w[2])
+        same = (g[2].numpy() == w[2].numpy())
+        assert same.mean() > 0.98
+        assert np.abs(g[0].numpy()[same] - w[0].numpy()[same]).max() <= 1e-4 * max(1.0, float(w[0].abs().max()))
+    assert list(sweep.infer_many(iter([]))) == [] and len(list(sweep.infer_many(iter(frames[:1])))) == 1
+    assert len(list(sweep.infer_many(iter(frames[:3])))) == 3
