@@ -575,7 +575,7 @@ def main():
                 kname += " (wide layers) + wm::conv_wm_kernel (16/32-channel layers, %.3f ms)" % wm_ms
             sparse_roof = {"bound": "tensor", "kernel": kname + " (the 20 tensor-core sparse convs of one frame)",
                            "achieved": ach, "peak": bf16_peak, "unit": "TFLOP/s", "frac": ach / bf16_peak,
-                           "traffic": ncu_dram_bytes("r02_f16_ncu_metrics.csv"), "algorithmic_flops": tc_flops, "ms": tc_ms,
+                           "traffic": ncu_dram_bytes("r02_sparse_ncu_metrics.csv"), "algorithmic_flops": tc_flops, "ms": tc_ms,
                            "peak_source": tpeak_src,
                            "note": "achieved counts ALGORITHMIC flops 2*pairs*Cin*Cout; the kernels execute 3 fp16 MMAs per "
                                    "product on zero-padded row tiles; bound by the row gather (tcgen05 kernel: L1TEX wavefronts "

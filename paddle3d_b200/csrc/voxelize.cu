@@ -314,7 +314,10 @@ __global__ void __launch_bounds__(256) vox_slots_kernel(const int32_t *__restric
   if (s >= P) return;
   int cur = i;
   for (; s < P; ++s) {
-    if (__ldcg(L + s) < cur) continue;  // resident is already smaller: it can only shrink further (monotone), skip the atomic
+    // plain (L1-cached, possibly stale) read: entries only shrink, so a stale "already smaller" is still true and the
+    // atomic can be skipped at L1 latency; a stale "larger" merely costs the atomic, which returns the fresh value
+    // (with ld.cg here every level walked cost an L2 round trip: the P = 64 pillar config went from 348 to 477 us)
+    if (L[s] < cur) continue;
     const int old = atomicMin(&L[s], cur);
     if (old == kInf) break;     // landed in a free slot
     if (old > cur) cur = old;   // displaced a larger index: carry it down

@@ -483,6 +483,42 @@ PD_BUILD_OP(p3d_sparse_conv_f16)
     .SetInferShapeFn(PD_INFER_SHAPE(ScF16InferShape))
     .SetInferDtypeFn(PD_INFER_DTYPE(ScF16InferDtype));
 
+// The same layer on the narrow-layer warp-MMA kernel (csrc/sparse_conv_wm.cu): (cin, cout) in {(16,16), (16,32), (32,32)}.
+// WEIGHT is the packed image of p3d_sparse_conv_wm_pack_weights; everything else as p3d_sparse_conv_f16.
+std::vector<paddle::Tensor> p3d_sparse_conv_wm_op(const paddle::Tensor &in, const paddle::Tensor &nbr, const paddle::Tensor &num,
+                                                  const paddle::Tensor &weight, const paddle::Tensor &scale,
+                                                  const paddle::Tensor &shift, const paddle::Tensor &residual,
+                                                  const paddle::Tensor &status, const int cin, const int cout, const int relu,
+                                                  const int want_f32) {
+  P3D_CHECK_GPU(in);
+  const int64_t cap = nbr.shape()[0];
+  const int K = static_cast<int>(nbr.shape()[1]);
+  auto out = want_f32 ? paddle::empty({cap, cout}, paddle::DataType::FLOAT32, paddle::GPUPlace())
+                      : paddle::empty({cap, 2 * cout}, paddle::DataType::FLOAT16, paddle::GPUPlace());
+  const size_t ws_bytes = p3d_sparse_conv_wm_workspace_bytes(cap, cout);
+  // the ticket head of the workspace must be zero on first use: paddle::full, not empty
+  auto ws = paddle::full({static_cast<int64_t>(ws_bytes ? ws_bytes : 16)}, 0, paddle::DataType::UINT8, paddle::GPUPlace());
+  const void *res = residual.numel() > 1 ? residual.data() : nullptr;
+  P3D_CALL(p3d_sparse_conv_wm(in.data(), nbr.data<int>(), num.data<int>(), cap, K, cin, cout, weight.data(), scale.data<float>(),
+                              shift.data<float>(), res, relu, want_f32 ? out.data<float>() : nullptr,
+                              want_f32 ? nullptr : out.data(), ws.data<uint8_t>(), ws_bytes,
+                              const_cast<int *>(status.data<int>()), in.stream()));
+  return {out};
+}
+std::vector<std::vector<int64_t>> ScWmInferShape(std::vector<int64_t> in, std::vector<int64_t> nbr, std::vector<int64_t> num,
+                                                 std::vector<int64_t> w, std::vector<int64_t> sc, std::vector<int64_t> sh,
+                                                 std::vector<int64_t> res, std::vector<int64_t> st, const int &cin,
+                                                 const int &cout, const int &relu, const int &want_f32) {
+  return {{nbr[0], want_f32 ? static_cast<int64_t>(cout) : static_cast<int64_t>(2 * cout)}};
+}
+PD_BUILD_OP(p3d_sparse_conv_wm)
+    .Inputs({"IN", "NBR", "NUM", "WEIGHT", "SCALE", "SHIFT", "RESIDUAL", "STATUS"})
+    .Outputs({"OUT"})
+    .Attrs({"cin: int", "cout: int", "relu: int", "want_f32: int"})
+    .SetKernelFn(PD_KERNEL(p3d_sparse_conv_wm_op))
+    .SetInferShapeFn(PD_INFER_SHAPE(ScWmInferShape))
+    .SetInferDtypeFn(PD_INFER_DTYPE(ScF16InferDtype));
+
 // dense Conv2D / Conv2DTranspose + BatchNorm2D(eval) + ReLU on pixel fp16-pair rows (second_backbone.py:72-120,
 // second_fpn.py:99-160, center_head.py:43-220).  IMAGE [B*H*W, 2*Cin] FLOAT16; WEIGHT = packed image
 // (p3d_dense_conv2d_f16_pack_weights per N tile).  Output rows have out_channels channels, this layer writes
