@@ -340,18 +340,28 @@ def _affine_act(x, scale, shift, residual, relu):
     return SparseCooTensor(x.index, values=out, channels=x.channels)
 
 
+def _fuse(x, **changes):
+    """A NEW lazy tensor whose pending kernel is x's with `changes` folded in.  x itself is left as it was (the
+    fusing layers used to edit x._pending in place, so `y = relu(x)` also changed x and add() turned y into y + x for
+    anyone still holding it); if x is consumed as well it simply launches its own, unfused kernel."""
+    q = _Pending()
+    for k in _Pending.__slots__:
+        setattr(q, k, getattr(x._pending, k, None))
+    for k, v in changes.items():
+        setattr(q, k, v)
+    return SparseCooTensor(x.index, channels=x.channels, pending=q)
+
+
 def add(x, y):
     """paddle.sparse.add for tensors over the same index set (sparse_resnet.py:108)."""
     if x.index is not y.index:
         raise NotImplementedError("sparse add over different index sets is outside the hot path")
     p = x._pending
     if p is not None and p.residual is None and not p.relu:
-        p.residual = y
-        return x
+        return _fuse(x, residual=y)
     p = y._pending
     if p is not None and p.residual is None and not p.relu:
-        p.residual = x
-        return y
+        return _fuse(y, residual=x)
     return _affine_act(x, None, None, y, False)
 
 
@@ -546,9 +556,7 @@ class BatchNorm(_Layer):
                 if key not in self._bias_fold:
                     self._bias_fold[key] = (p.shift.double() * scale.double() + shift.double()).float().contiguous()
                 shift = self._bias_fold[key]
-            p.shift = shift
-            p.scale = scale
-            return x
+            return _fuse(x, shift=shift, scale=scale)
         return _affine_act(x, scale, shift, None, False)
 
 
@@ -556,8 +564,7 @@ class ReLU(_Layer):
     def forward(self, x):
         p = x._pending
         if p is not None:
-            p.relu = True
-            return x
+            return _fuse(x, relu=True)
         return _affine_act(x, None, None, None, True)
 
 

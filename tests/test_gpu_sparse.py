@@ -351,3 +351,30 @@ def test_h16_rows_roundtrip_and_range_flag(cuda):
         tx[5, 3] = 1e6
         check(L.p3d_rows_convert_h16(ptr(tx), 1, None, 1000, C, ptr(h), ptr(status), stream(cuda)), "to_h16")
         assert int(status[0]) == 1
+
+
+def test_lazy_fusion_does_not_mutate_its_input(cuda, oracle_mod):
+    """conv -> bn -> add -> relu fold into one launch WITHOUT editing the tensors they were given: a consumer
+    that kept the conv output still reads the plain convolution."""
+    import torch
+    from paddle3d_b200.ops import sparse_nn as sp
+    rng = np.random.default_rng(11)
+    B, D, H, W = 1, 7, 20, 21
+    coords = _rand_sites(rng, B, D, H, W, 0.15)
+    feats = rng.normal(size=(len(coords), 16)).astype(np.float32)
+    conv = sp.SubmConv3D(16, 16, 3, padding=1, bias_attr=False).init_parameters(rng, cuda)
+    conv.precision = sp.F16X3
+    bn = sp.BatchNorm(16, epsilon=1e-3).init_parameters(rng, cuda, randomize=True)
+    x = sp.sparse_coo_tensor(_t(cuda, coords).t(), _t(cuda, feats), [B, D, H, W, 16])
+    c = conv(x)
+    y = sp.ReLU()(sp.add(bn(c), x))
+    assert y is not c and c._pending is not None and c._pending.scale is None and not c._pending.relu and c._pending.residual is None
+    n = y.nnz()
+    plain = c.values().cpu().numpy()[:n]      # the un-fused convolution
+    fused = y.values().cpu().numpy()[:n]
+    _, of, _, _ = oracle_mod.sparse_conv3d(coords, feats, B, (D, H, W), conv.weight.cpu().numpy(), conv.stride, conv.padding, True)
+    rel_check('unfused conv kept by an earlier consumer', plain, of)
+    want = oracle_mod.bn_relu(of, bn.weight.cpu().numpy(), bn.bias.cpu().numpy(), bn._mean.cpu().numpy(),
+                              bn._variance.cpu().numpy(), 1e-3, relu=True, residual=feats)
+    rel_check('fused conv + bn + add + relu', fused, want)
+    assert plain.min() < 0 <= fused.min()
