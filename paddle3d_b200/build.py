@@ -11,7 +11,7 @@ OBJ = os.path.join(CSRC, "_obj")
 LIB = os.path.join(HERE, "libp3d_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-Xcompiler", "-fPIC",
-         "-I", os.path.join(ROOT, "include"), "-I", CSRC]
+         "-I", os.path.join(ROOT, "include"), "-I", CSRC] + os.environ.get("P3D_NVCC_EXTRA", "").split()
 
 
 def _newer(src, dst, deps):

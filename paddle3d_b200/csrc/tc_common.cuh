@@ -25,6 +25,9 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
+#ifndef P3D_MBAR_HINT_NS
+#define P3D_MBAR_HINT_NS 20000  // suspend-time hint of mbarrier.try_wait (ns); build with -DP3D_MBAR_HINT_NS=.. to experiment
+#endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   // try_wait with a suspend-time hint: the thread sleeps in hardware until the phase completes (or ~20 us pass)
   // instead of polling - with the short default limit the waiting warps executed ~70 % of all instructions of the
@@ -37,7 +40,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.u32 %0, 1, 0, p;\n\t}"
         : "=r"(done)
-        : "r"(bar), "r"(parity), "r"(20000u)
+        : "r"(bar), "r"(parity), "r"(static_cast<uint32_t>(P3D_MBAR_HINT_NS))
         : "memory");
     if (!done && ++spins > 200000) __trap();  // seconds: a protocol bug must not hang the GPU
   } while (!done);
