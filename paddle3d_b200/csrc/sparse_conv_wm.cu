@@ -482,7 +482,7 @@ extern "C" int p3d_sparse_conv_wm(const void *in_h16, const int32_t *nbr, const 
   if (n_out_cap == 0) return P3D_OK;
   if ((reinterpret_cast<uintptr_t>(in_h16) & 15) || (reinterpret_cast<uintptr_t>(out_f32) & 15) ||
       (reinterpret_cast<uintptr_t>(out_h16) & 15) || (reinterpret_cast<uintptr_t>(packed_weight) & 15) ||
-      (reinterpret_cast<uintptr_t>(residual_h16) & 15) || (reinterpret_cast<uintptr_t>(nbr) & 3) ||
+      (reinterpret_cast<uintptr_t>(residual_h16) & 15) || (reinterpret_cast<uintptr_t>(nbr) & 15) ||  // 16-byte cp.async
       (reinterpret_cast<uintptr_t>(workspace) & 15))
     return P3D_ERR_INVALID_ARG;
   if (!workspace || workspace_bytes < p3d_sparse_conv_wm_workspace_bytes(n_out_cap, Cout)) return P3D_ERR_WORKSPACE;

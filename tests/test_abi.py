@@ -91,6 +91,14 @@ def test_invalid_arguments_of_the_conv_entry_points():
     assert L.p3d_sparse_conv_gather_gemm_split_tma(p, 128, p, None, 128, 27, 16, 16, p, None, None, None, 0, p, None, None, 0, None) == -4
     assert L.p3d_sparse_conv_packed_weight_bytes(27, 5, 16) == 0 and L.p3d_sparse_conv_packed_weight_bytes(27, 16, 16) > 0
     assert L.p3d_rows_convert_layout(p, 2, None, 16, 16, p, None) == -1
+    # narrow-layer warp-MMA conv: unsupported shape, missing output, misaligned neighbour map, missing / short workspace
+    wm = L.p3d_sparse_conv_wm
+    assert wm(p, p, None, 128, 27, 64, 64, p, None, None, None, 0, p, None, p, 1 << 30, None, None) == -4
+    assert wm(p, p, None, 128, 27, 16, 16, p, None, None, None, 0, None, None, p, 1 << 30, None, None) == -1
+    assert wm(p, odd, None, 128, 27, 16, 16, p, None, None, None, 0, p, None, p, 1 << 30, None, None) == -1
+    assert wm(p, p, None, 128, 27, 16, 16, p, None, None, None, 0, p, None, None, 0, None, None) == -2
+    assert wm(p, p, None, 128, 27, 16, 16, p, None, None, None, 0, p, None, p, 16, None, None) == -2
+    assert wm(p, p, None, 0, 27, 16, 16, p, None, None, None, 0, p, None, None, 0, None, None) == 0  # empty input: nothing to do
     # dense conv: channel counts, N tile, transposed-conv geometry, split-row output columns
     ok = dict(B=1, H=8, W=8)
     assert L.p3d_dense_conv2d_split(p, 1, 8, 8, 48, p, 64, 64, 3, 3, 1, 1, 1, None, None, 0, p, 64, 0, None, None) == -4
