@@ -244,6 +244,24 @@ def ncu_dram_bytes(path_name):
         return None  # a malformed capture must not take the benchmark down
 
 
+def ncu_tensor_active(path_name):
+    """Time-weighted sm__pipe_tensor_cycles_active (% of peak sustained active) over the launches of a committed ncu capture
+    (tcgen05 and legacy HMMA launches alike); None when the capture is not in the tree."""
+    import csv
+    path = os.path.join(ROOT, "profiles", path_name)
+    if not os.path.exists(path):
+        return None
+    try:
+        rows = list(csv.reader(open(path)))
+        hdr = rows[0]
+        it, ia = hdr.index("gpu__time_duration.sum"), hdr.index("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active")
+        t = [float(r[it]) for r in rows[2:]]
+        a = [float(r[ia]) for r in rows[2:]]
+        return sum(x * y for x, y in zip(t, a)) / sum(t) if sum(t) > 0 else None
+    except (ValueError, KeyError, IndexError, OSError):
+        return None
+
+
 def dense_flops(net, H, W):
     """Algorithmic flops (2 x MACs) of the dense RPN / neck / CenterHead at a BEV of H x W."""
     total, h, w = 0.0, H, W
@@ -575,7 +593,9 @@ def main():
                 kname += " (wide layers) + wm::conv_wm_kernel (16/32-channel layers, %.3f ms)" % wm_ms
             sparse_roof = {"bound": "tensor", "kernel": kname + " (the 20 tensor-core sparse convs of one frame)",
                            "achieved": ach, "peak": bf16_peak, "unit": "TFLOP/s", "frac": ach / bf16_peak,
-                           "traffic": ncu_dram_bytes("r02_sparse_ncu_metrics.csv"), "algorithmic_flops": tc_flops, "ms": tc_ms,
+                           "traffic": ncu_dram_bytes("r02_sparse_ncu_metrics.csv"),
+                           "tensor_pipe_active_pct_ncu": ncu_tensor_active("r02_sparse_ncu_metrics.csv"),
+                           "algorithmic_flops": tc_flops, "ms": tc_ms,
                            "peak_source": tpeak_src,
                            "note": "achieved counts ALGORITHMIC flops 2*pairs*Cin*Cout; the kernels execute 3 fp16 MMAs per "
                                    "product on zero-padded row tiles; bound by the row gather (tcgen05 kernel: L1TEX wavefronts "
@@ -594,7 +614,9 @@ def main():
             ach = fl / (ms_dense * 1e-3) / 1e12
             dense_roof = {"bound": "tensor", "kernel": "dcf::dense_conv_f16_kernel (RPN + neck + CenterHead: 16 + 1 + 1 launches)",
                           "achieved": ach, "peak": bf16_peak, "unit": "TFLOP/s", "frac": ach / bf16_peak,
-                          "traffic": ncu_dram_bytes("r02_dense_ncu_metrics.csv"), "algorithmic_flops": fl, "ms": ms_dense,
+                          "traffic": ncu_dram_bytes("r02_dense_ncu_metrics.csv"),
+                          "tensor_pipe_active_pct_ncu": ncu_tensor_active("r02_dense_ncu_metrics.csv"),
+                          "algorithmic_flops": fl, "ms": ms_dense,
                           "peak_source": tpeak_src,
                           "note": "achieved counts ALGORITHMIC flops (2 x MACs of the convolutions); the kernel executes 3 fp16 "
                                   "MMAs per product (fp16-pair operands, 1e-4 parity), i.e. the tensor pipe runs at 3 x "
