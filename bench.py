@@ -13,9 +13,9 @@ measured in the same run and reported under `geometry_01m` (--geometry 01 swaps 
 round-1 workload (resident synthetic head tensors).
 
 `value`  : frames/s with the frame's points already resident in HBM (CUDA-graph replay per frame), --in-flight frames
-           (default 3) computing concurrently per GPU: CenterPointSweep lanes with their own buffers / graph / stream and a
-           shared model (measured: 605 / 709 / 739 frames/s with 1 / 2 / 3 lanes - the latency-bound kernels of one frame
-           fill the SMs the other frames leave idle).
+           (default 4) computing concurrently per GPU: CenterPointSweep lanes with their own buffers / graph / stream and a
+           shared model (measured: 605 / 709 / 740 / 754 / 735 frames/s with 1 / 2 / 3 / 4 / 6 lanes - the latency-bound
+           kernels of one frame fill the SMs the other frames leave idle).
 `e2e`    : frames/s through the public API CenterPointSweep.infer_many(): pinned-host points -> H2D ->
            graph -> D2H of boxes/scores/labels/counts/status, every step; the H2D of a lane's next frame overlaps its
            compute (copy stream + two staging buffers per lane). `e2e.sync_value` is the one-frame-at-a-time
@@ -48,7 +48,7 @@ BN_GAIN = 6.0 ** 0.5  # seeded weights with BatchNorm gamma = sqrt(6): activatio
 POOL = 32  # distinct frames cycled through: 32 x 6 MB = 192 MB of inputs > 126 MB L2
 
 
-def make_config(geometry, with_head, in_flight=3):
+def make_config(geometry, with_head, in_flight=4):
     """The `config` object both arms print (identical dicts: the driver compares them)."""
     geo = "0.075 m voxels / +-54 m range" if geometry == "0075" else "0.1 m voxels / +-72 m range"
     return {"workload": WORKLOAD % (geo, HEAD_ON if with_head else HEAD_OFF), "geometry": geometry, "with_head": bool(with_head),
@@ -432,7 +432,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-head", action="store_true", help="skip the dense RPN / neck / CenterHead (round-1 workload)")
     ap.add_argument("--no-second-geometry", action="store_true")
-    ap.add_argument("--in-flight", type=int, default=3, help="frames computing concurrently per GPU (CenterPointSweep lanes)")
+    ap.add_argument("--in-flight", type=int, default=4, help="frames computing concurrently per GPU (CenterPointSweep lanes)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
