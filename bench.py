@@ -627,8 +627,9 @@ def main():
             extra["roofline"] = cands[0]
             rooflines = cands[1:] + rooflines
         extra["rooflines_other"] = rooflines
-        # CPU baseline on a bounded sample: one full frame through the oracle port
-        if not args.no_cpu_baseline:
+        # CPU baseline on a bounded sample: one full frame through the oracle port (N = 1 only: under torchrun the ranks
+        # share the host cores and OMP_NUM_THREADS is 1; `--impl reference` is the CPU arm of the scaling runs)
+        if not args.no_cpu_baseline and world == 1:
             import oracle
             dense_w = pipe.dense.export_numpy() if pipe.dense is not None else None
             cf = build_cpu_frame(cfg, with_head, pipe.export_weights_numpy(), dense_w, pipe.head_host)
