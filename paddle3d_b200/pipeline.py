@@ -329,9 +329,29 @@ class CenterPointSweep:
         for p in self.lanes:
             p.stream.synchronize()
 
+    @staticmethod
+    def _lane_slot(i, lanes):
+        return i % lanes, (i // lanes) & 1
+
+    @staticmethod
+    def plan(n_frames, lanes):
+        """The order of operations of infer_many for a sweep of n_frames: ("submit", frame, lane, slot) / ("result", frame,
+        lane, slot) tuples.  Frame i runs on lane i % lanes, slot (i // lanes) & 1; at most lanes + 1 frames are
+        outstanding, and the result of a frame is always read before its (lane, slot) is submitted again
+        (tests/test_sweep_plan.py checks these invariants without a GPU)."""
+        import collections
+        pending = collections.deque()
+        for i in range(n_frames):
+            pending.append((i,) + CenterPointSweep._lane_slot(i, lanes))
+            yield ("submit",) + pending[-1]
+            if len(pending) > lanes:
+                yield ("result",) + pending.popleft()
+        while pending:
+            yield ("result",) + pending.popleft()
+
     def infer_many(self, frames_host):
         """As CenterPointHotPath.infer_many (pinned host frames in, host results out, in order), with len(self) frames
-        computing concurrently: frame i runs on lane i % lanes, slot (i // lanes) & 1."""
+        computing concurrently: frame i runs on lane i % lanes, slot (i // lanes) & 1 (see plan())."""
         import collections
         L = len(self.lanes)
         for p in self.lanes:
@@ -340,7 +360,8 @@ class CenterPointSweep:
             p.prepare_sweep()
         pending = collections.deque()
         for i, pts in enumerate(frames_host):
-            lane, k = self.lanes[i % L], (i // L) & 1
+            li, k = self._lane_slot(i, L)
+            lane = self.lanes[li]
             lane._submit(pts, k, i < 2 * L)
             pending.append((lane, k))
             if len(pending) > L:
