@@ -9,7 +9,6 @@ signature is arrays (`hard_voxelize`, `boxes_iou_bev`, `nms_gpu`).  `import padd
 """
 import ctypes as C
 import ctypes.util
-import os
 
 import numpy as np
 
